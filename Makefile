@@ -1,0 +1,44 @@
+# Builds libmpc_b200.so (CUDA kernels + C ABI, sm_100a only), the host CLI `compressor` (drop-in for the
+# reference binary that bin/run invokes) and the CPU oracle used by the tests.
+PKG      := cal_22-mpc_b200
+CSRC     := $(PKG)/csrc
+HOST     := $(PKG)/host
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CXX      := /usr/bin/g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -I$(CSRC) --expt-relaxed-constexpr
+CXXFLAGS := -O3 -std=c++17 -fPIC -Iinclude -I$(CSRC) -Wall
+
+LIB      := $(PKG)/libmpc_b200.so
+CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu
+CU_OBJS  := $(CU_SRCS:.cu=.o)
+CC_OBJS  := $(CSRC)/mpc_config.o
+
+all: $(LIB) compressor oracle
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(CSRC)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h include/*.h)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(CC_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -Xlinker --no-undefined
+
+HOST_SRCS := $(wildcard $(HOST)/*.cpp $(HOST)/compressor/*.cpp $(HOST)/loader/*.cpp)
+compressor: $(HOST_SRCS) $(wildcard $(HOST)/*.h $(HOST)/compressor/*.h $(HOST)/loader/*.h) $(LIB)
+	@if [ -n "$(HOST_SRCS)" ]; then \
+	  $(CXX) $(CXXFLAGS) -I$(HOST) $(HOST_SRCS) -o bin/compressor -L$(PKG) -lmpc_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lpthread; \
+	fi
+
+oracle:
+	$(MAKE) -C oracle
+
+sass: $(LIB)
+	cuobjdump -sass $(LIB) > profiles/libmpc_b200.sass
+
+clean:
+	rm -f $(CSRC)/*.o $(LIB) bin/compressor
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean sass

@@ -1,0 +1,221 @@
+"""ctypes binding of libmpc_b200.so (include/mpc_capi.h).
+
+Thin by design: the product is the CUDA library behind the C ABI; this module only lets
+tests/ and bench.py drive it from Python.  There is no Python or CPU implementation of the
+path here -- if the shared library or a CUDA device is missing, calls raise MpcError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_LINE = 128
+MAX_MODULES = 16
+HIST_BINS = 8 * MAX_LINE + 32
+STATS_WORDS = 2 * (MAX_MODULES + 1) + (MAX_MODULES + 1) * HIST_BINS
+
+SYN = {"zero": 0, "wordsame": 1, "smooth_f32": 2, "ramp_i32": 3, "pointer": 4, "random": 5,
+       "sparse_i32": 6, "noisy_f32": 7, "mixed_hashed": 8, "mixed_regions": 9}
+
+
+class ModulePod(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("predictor", C.c_int32), ("root", C.c_int32),
+                ("consecutive_xor", C.c_int32), ("table_size", C.c_int32),
+                ("base", C.c_uint8 * MAX_LINE), ("diff", C.c_uint8 * MAX_LINE), ("shift", C.c_int8 * MAX_LINE),
+                ("scan_row", C.c_uint8 * (8 * MAX_LINE)), ("scan_col", C.c_uint8 * (8 * MAX_LINE))]
+
+
+class ConfigPod(C.Structure):
+    _fields_ = [("line_size", C.c_int32), ("num_modules", C.c_int32), ("has_wordsame", C.c_int32),
+                ("first_predcomp", C.c_int32), ("enc_bits", C.c_int32 * (MAX_MODULES + 1)),
+                ("modules", ModulePod * MAX_MODULES)]
+
+
+class StatsPod(C.Structure):
+    _fields_ = [("blocks", C.c_uint64), ("original_bits", C.c_uint64), ("compressed_bits", C.c_uint64),
+                ("count", C.c_uint64 * (MAX_MODULES + 1)), ("comp_bits", C.c_uint64 * (MAX_MODULES + 1)),
+                ("res_lines", C.c_uint64 * (MAX_MODULES + 1)), ("res_abs", C.c_uint64 * (MAX_MODULES + 1)),
+                ("res_sq", C.c_uint64 * (MAX_MODULES + 1)),
+                ("hist", (C.c_uint64 * HIST_BINS) * (MAX_MODULES + 1))]
+
+
+class MpcError(RuntimeError):
+    pass
+
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpc_b200.so")
+
+# every symbol include/mpc_capi.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config_validate", "mpc_create",
+           "mpc_destroy", "mpc_last_error", "mpc_global_error", "mpc_set_kernel", "mpc_kernel_name", "mpc_set_stream",
+           "mpc_submit_device", "mpc_submit_host", "mpc_sync", "mpc_stats_device_ptr", "mpc_finish",
+           "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version"]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise MpcError(f"{LIB_PATH} is missing: build it with `make` (nvcc, sm_100a); there is no fallback path")
+    l = C.CDLL(LIB_PATH)
+    vp, u64, sz = C.c_void_p, C.c_uint64, C.c_size_t
+    l.mpc_config_from_json_file.argtypes = [C.c_char_p, C.POINTER(ConfigPod), C.c_char_p, sz]
+    l.mpc_config_from_json_text.argtypes = [C.c_char_p, C.POINTER(ConfigPod), C.c_char_p, sz]
+    l.mpc_config_validate.argtypes = [C.POINTER(ConfigPod), C.c_char_p, sz]
+    l.mpc_create.argtypes = [C.POINTER(ConfigPod), C.c_int, C.POINTER(vp)]
+    l.mpc_destroy.argtypes = [vp]
+    l.mpc_destroy.restype = None
+    l.mpc_last_error.argtypes = [vp]
+    l.mpc_last_error.restype = C.c_char_p
+    l.mpc_global_error.restype = C.c_char_p
+    l.mpc_set_kernel.argtypes = [vp, C.c_int]
+    l.mpc_kernel_name.argtypes = [vp]
+    l.mpc_set_stream.argtypes = [vp, vp]
+    l.mpc_kernel_name.restype = C.c_char_p
+    l.mpc_submit_device.argtypes = [vp, vp, u64, vp]
+    l.mpc_submit_host.argtypes = [vp, vp, u64, vp]
+    l.mpc_sync.argtypes = [vp]
+    l.mpc_stats_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    l.mpc_finish.argtypes = [vp, C.POINTER(StatsPod)]
+    l.mpc_stats_expand.argtypes = [C.POINTER(ConfigPod), vp, sz, C.POINTER(StatsPod)]
+    l.mpc_reset.argtypes = [vp]
+    l.mpc_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    l.mpc_synth_device.argtypes = [vp, vp, u64, u64, u64, C.c_int, u64]
+    l.mpc_version.restype = C.c_char_p
+    _LIB = l
+    return l
+
+
+def load_config(path=None, text=None):
+    """JSON (reference format, VPC.cpp:72-330) -> ConfigPod; raises MpcError with the library's message."""
+    pod = ConfigPod()
+    err = C.create_string_buffer(1024)
+    if path is not None:
+        rc = lib().mpc_config_from_json_file(os.fsencode(path), C.byref(pod), err, 1024)
+    else:
+        rc = lib().mpc_config_from_json_text(text.encode(), C.byref(pod), err, 1024)
+    if rc != 0:
+        raise MpcError(f"config rejected ({rc}): {err.value.decode(errors='replace')}")
+    return pod
+
+
+class Stats:
+    """Expanded statistics; field names follow comp::VPCResult / comp::CompResult."""
+
+    def __init__(self, pod, num_modules, line_size):
+        k = num_modules + 1
+        self.blocks = int(pod.blocks)
+        self.OriginalSize = int(pod.original_bits)
+        self.CompressedSize = int(pod.compressed_bits)
+        self.count = np.array(pod.count[:k], dtype=np.uint64)
+        self.comp_bits = np.array(pod.comp_bits[:k], dtype=np.uint64)
+        self.res_lines = np.array(pod.res_lines[:k], dtype=np.uint64)
+        self.res_abs = np.array(pod.res_abs[:k], dtype=np.uint64)
+        self.res_sq = np.array(pod.res_sq[:k], dtype=np.uint64)
+        self.hist = np.ctypeslib.as_array(pod.hist)[:k].copy()
+        self.line_size = line_size
+
+    @property
+    def CompRatio(self):  # CompResult.h:34
+        return float(self.OriginalSize) / float(self.CompressedSize) if self.CompressedSize else float("nan")
+
+    def mae(self, k):  # VPC.h:62-76 with the exact reformulation of SURVEY.md section 7
+        n = int(self.res_lines[k])
+        return (float(int(self.res_abs[k])) / self.line_size) / float(n) if n else 0.0
+
+    def mse(self, k):
+        n = int(self.res_lines[k])
+        return (float(int(self.res_sq[k])) / self.line_size) / float(n) if n else 0.0
+
+
+class Mpc:
+    """One context = one GPU (mpc_create .. mpc_destroy)."""
+
+    def __init__(self, config, device=0):
+        self.cfg = config if isinstance(config, ConfigPod) else load_config(path=config)
+        h = C.c_void_p()
+        rc = lib().mpc_create(C.byref(self.cfg), device, C.byref(h))
+        if rc != 0:
+            raise MpcError(f"mpc_create failed ({rc}): {lib().mpc_global_error().decode()}")
+        self.h = h
+        self.line_size = self.cfg.line_size
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MpcError(f"libmpc_b200 error {rc}: {lib().mpc_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mpc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_kernel(self, which):
+        self._check(lib().mpc_set_kernel(self.h, which))
+
+    def set_stream(self, cuda_stream):
+        self._check(lib().mpc_set_stream(self.h, cuda_stream))
+
+    def kernel_name(self):
+        return lib().mpc_kernel_name(self.h).decode()
+
+    def submit_device(self, d_lines_ptr, n_blocks, d_packed_ptr=None):
+        self._check(lib().mpc_submit_device(self.h, d_lines_ptr, n_blocks, d_packed_ptr))
+
+    def submit_host(self, lines, packed=None):
+        lines = np.ascontiguousarray(lines, dtype=np.uint8)
+        n = lines.size // self.line_size
+        pp = packed.ctypes.data if packed is not None else None
+        self._keep = (lines, packed)
+        self._check(lib().mpc_submit_host(self.h, lines.ctypes.data, n, pp))
+
+    def submit_host_ptr(self, ptr, n_blocks, packed_ptr=None):
+        self._check(lib().mpc_submit_host(self.h, ptr, n_blocks, packed_ptr))
+
+    def sync(self):
+        self._check(lib().mpc_sync(self.h))
+
+    def reset(self):
+        self._check(lib().mpc_reset(self.h))
+
+    def finish(self):
+        pod = StatsPod()
+        self._check(lib().mpc_finish(self.h, C.byref(pod)))
+        return Stats(pod, self.cfg.num_modules, self.line_size)
+
+    def stats_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(lib().mpc_stats_device_ptr(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def expand(self, words):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        pod = StatsPod()
+        self._check(lib().mpc_stats_expand(C.byref(self.cfg), words.ctypes.data, words.size, C.byref(pod)))
+        return Stats(pod, self.cfg.num_modules, self.line_size)
+
+    def last_timing(self):
+        ms, n = C.c_float(), C.c_int()
+        self._check(lib().mpc_last_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def synth_device(self, d_ptr, first_block, n_blocks, total_blocks, kind, seed):
+        k = SYN[kind] if isinstance(kind, str) else kind
+        self._check(lib().mpc_synth_device(self.h, d_ptr, first_block, n_blocks, total_blocks, k, seed))
+
+    def compress(self, lines):
+        """Convenience: host array of blocks -> (sizes, selected) per block + Stats (fresh statistics)."""
+        lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, self.line_size)
+        packed = np.zeros(lines.shape[0], dtype=np.uint16)
+        self.reset()
+        self.submit_host(lines, packed)
+        st = self.finish()
+        return (packed & 0x7FF).astype(np.uint32), (packed >> 11).astype(np.int32) - 1, st
+
+
+def unpack(packed):
+    packed = np.asarray(packed, dtype=np.uint16)
+    return (packed & 0x7FF).astype(np.uint32), (packed >> 11).astype(np.int32) - 1

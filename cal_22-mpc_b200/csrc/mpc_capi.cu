@@ -1,0 +1,368 @@
+// C-ABI of libmpc_b200 (include/mpc_capi.h): context, streams, the chunked host->device loader and
+// the statistics vector.  Replaces the per-line driver loop of the reference
+// (src/main.cpp:229-244: GetCacheline -> CompressLine -> VPCResult::Update) with batched launches.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mpc_capi.h"
+#include "mpc_internal.h"
+#include "mpc_spec.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+struct Stage {             // one half of the double buffer used by mpc_submit_host
+  cudaStream_t stream = nullptr;
+  uint8_t* h_pinned = nullptr;
+  uint8_t* d_lines = nullptr;
+  uint16_t* d_packed = nullptr;
+  uint16_t* h_packed = nullptr;  // pinned
+  cudaEvent_t k_start = nullptr, k_stop = nullptr, done = nullptr;
+  bool busy = false;
+  // pending result copy (pinned -> user buffer) performed on the host once `done` fires
+  uint16_t* user_packed = nullptr;
+  uint64_t user_count = 0;
+};
+
+}  // namespace
+
+struct mpc_ctx {
+  mpc_config_pod cfg;
+  int device = 0;
+  int sm_count = 148;
+  mpc::GenericParams gparams;
+  mpc::GenericModule* d_gmods = nullptr;
+  const mpc::SpecKernel* spec = nullptr;  // specialised kernel matching cfg, if any
+  int kernel_choice = 0;
+  uint64_t* d_stats = nullptr;
+  cudaStream_t own_stream = nullptr;      // created by mpc_create
+  cudaStream_t stream = nullptr;          // stream used by mpc_submit_device / synth / stats (own or caller's)
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_order = nullptr;
+  Stage stage[2];
+  uint64_t chunk_blocks = 0;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  bool last_timing_pending = false;       // ev_start/ev_stop recorded but not read yet
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_host_events;
+  std::string error;
+  std::string kernel_name;
+};
+
+namespace {
+
+int fail(mpc_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->error = buf;
+  g_error = buf;
+  return code;
+}
+
+#define MPC_CUDA(ctx, call)                                                                           \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) return fail(ctx, MPC_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+bool use_spec(const mpc_ctx* ctx) {
+  if (ctx->kernel_choice == 1) return false;
+  return ctx->spec != nullptr;
+}
+
+void refresh_kernel_name(mpc_ctx* ctx) {
+  ctx->kernel_name = use_spec(ctx) ? (std::string("spec_thread:") + ctx->spec->name) : std::string("generic_warp");
+}
+
+int launch(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n, uint16_t* d_packed, cudaStream_t s) {
+  cudaError_t e;
+  if (use_spec(ctx))
+    e = ctx->spec->launch(ctx->cfg, d_lines, n, d_packed, ctx->d_stats, ctx->sm_count, s);
+  else
+    e = mpc::launch_generic(ctx->gparams, ctx->d_gmods, d_lines, n, d_packed, ctx->d_stats, ctx->sm_count, s);
+  if (e != cudaSuccess) return fail(ctx, MPC_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return MPC_OK;
+}
+
+int drain_stage(mpc_ctx* ctx, Stage& st) {
+  if (!st.busy) return MPC_OK;
+  MPC_CUDA(ctx, cudaEventSynchronize(st.done));
+  float ms = 0.f;
+  MPC_CUDA(ctx, cudaEventElapsedTime(&ms, st.k_start, st.k_stop));
+  ctx->last_ms += ms;
+  if (st.user_packed) memcpy(st.user_packed, st.h_packed, st.user_count * sizeof(uint16_t));
+  st.user_packed = nullptr;
+  st.busy = false;
+  return MPC_OK;
+}
+
+int ensure_stages(mpc_ctx* ctx) {
+  if (ctx->stage[0].stream) return MPC_OK;
+  ctx->chunk_blocks = (64ull << 20) / (uint64_t)ctx->cfg.line_size;  // 64 MiB per chunk
+  const size_t bytes = (size_t)ctx->chunk_blocks * ctx->cfg.line_size;
+  for (Stage& st : ctx->stage) {
+    MPC_CUDA(ctx, cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+    MPC_CUDA(ctx, cudaMallocHost(&st.h_pinned, bytes));
+    MPC_CUDA(ctx, cudaMalloc(&st.d_lines, bytes));
+    MPC_CUDA(ctx, cudaMalloc(&st.d_packed, ctx->chunk_blocks * sizeof(uint16_t)));
+    MPC_CUDA(ctx, cudaMallocHost(&st.h_packed, ctx->chunk_blocks * sizeof(uint16_t)));
+    MPC_CUDA(ctx, cudaEventCreate(&st.k_start));
+    MPC_CUDA(ctx, cudaEventCreate(&st.k_stop));
+    MPC_CUDA(ctx, cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  }
+  return MPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mpc_version(void) { return "mpc_b200 0.1 (sm_100a)"; }
+const char* mpc_global_error(void) { return g_error.c_str(); }
+const char* mpc_last_error(const mpc_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, MPC_E_ARG, "mpc_create: null argument");
+  char err[512] = {0};
+  int rc = mpc_config_validate(cfg, err, sizeof(err));
+  if (rc != MPC_OK) return fail(nullptr, rc, "%s", err);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, MPC_E_CUDA, "no CUDA device available (%s); libmpc_b200 has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, MPC_E_ARG, "device %d out of range (have %d)", device, ndev);
+  mpc_ctx* ctx = new mpc_ctx;
+  ctx->cfg = *cfg;
+  ctx->device = device;
+#define MPC_CREATE_CUDA(call)                                                                 \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      int rc__ = fail(nullptr, MPC_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));  \
+      mpc_destroy(ctx);                                                                       \
+      return rc__;                                                                            \
+    }                                                                                         \
+  } while (0)
+  MPC_CREATE_CUDA(cudaSetDevice(device));
+  MPC_CREATE_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  MPC_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  MPC_CREATE_CUDA(cudaEventCreate(&ctx->ev_start));
+  MPC_CREATE_CUDA(cudaEventCreate(&ctx->ev_stop));
+  MPC_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+  MPC_CREATE_CUDA(cudaMalloc(&ctx->d_stats, mpc::kStatsWords * sizeof(uint64_t)));
+  MPC_CREATE_CUDA(cudaMemsetAsync(ctx->d_stats, 0, mpc::kStatsWords * sizeof(uint64_t), ctx->stream));
+  std::vector<mpc::GenericModule> gm((size_t)MPC_MAX_MODULES);
+  mpc::build_generic_tables(ctx->cfg, &ctx->gparams, gm.data());
+  const size_t gbytes = sizeof(mpc::GenericModule) * (size_t)(ctx->gparams.num_predcomp > 0 ? ctx->gparams.num_predcomp : 1);
+  MPC_CREATE_CUDA(cudaMalloc(&ctx->d_gmods, gbytes));
+  MPC_CREATE_CUDA(cudaMemcpyAsync(ctx->d_gmods, gm.data(), gbytes, cudaMemcpyHostToDevice, ctx->stream));
+  MPC_CREATE_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef MPC_CREATE_CUDA
+  ctx->spec = mpc::find_spec_kernel(ctx->cfg);
+  refresh_kernel_name(ctx);
+  *out = ctx;
+  return MPC_OK;
+}
+
+void mpc_destroy(mpc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (Stage& st : ctx->stage) {
+    if (st.stream) cudaStreamDestroy(st.stream);
+    if (st.h_pinned) cudaFreeHost(st.h_pinned);
+    if (st.d_lines) cudaFree(st.d_lines);
+    if (st.d_packed) cudaFree(st.d_packed);
+    if (st.h_packed) cudaFreeHost(st.h_packed);
+    if (st.k_start) cudaEventDestroy(st.k_start);
+    if (st.k_stop) cudaEventDestroy(st.k_stop);
+    if (st.done) cudaEventDestroy(st.done);
+  }
+  if (ctx->d_gmods) cudaFree(ctx->d_gmods);
+  if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int mpc_set_kernel(mpc_ctx* ctx, int which) {
+  if (!ctx) return MPC_E_ARG;
+  if (which < 0 || which > 2) return fail(ctx, MPC_E_ARG, "mpc_set_kernel: which = %d", which);
+  if (which == 2 && !ctx->spec)
+    return fail(ctx, MPC_E_STATE, "no specialised kernel is built into this library for the given config");
+  ctx->kernel_choice = which;
+  refresh_kernel_name(ctx);
+  return MPC_OK;
+}
+
+const char* mpc_kernel_name(const mpc_ctx* ctx) { return ctx ? ctx->kernel_name.c_str() : ""; }
+
+int mpc_set_stream(mpc_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return MPC_E_ARG;
+  int rc = mpc_sync(ctx);
+  if (rc != MPC_OK) return rc;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return MPC_OK;
+}
+
+int mpc_submit_device(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed) {
+  if (!ctx) return MPC_E_ARG;
+  if (n_blocks && !d_lines) return fail(ctx, MPC_E_ARG, "mpc_submit_device: null lines");
+  if ((uintptr_t)d_lines & 15) return fail(ctx, MPC_E_ARG, "mpc_submit_device: lines must be 16-byte aligned");
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPC_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+  int rc = n_blocks ? launch(ctx, d_lines, n_blocks, d_packed, ctx->stream) : MPC_OK;
+  if (rc != MPC_OK) return rc;
+  MPC_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+  ctx->last_timing_pending = true;
+  ctx->last_launches = n_blocks ? 1 : 0;
+  return MPC_OK;
+}
+
+int mpc_submit_host(mpc_ctx* ctx, const uint8_t* h_lines, uint64_t n_blocks, uint16_t* h_packed) {
+  if (!ctx) return MPC_E_ARG;
+  if (n_blocks && !h_lines) return fail(ctx, MPC_E_ARG, "mpc_submit_host: null lines");
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_stages(ctx);
+  if (rc != MPC_OK) return rc;
+  // Statistics memset / earlier device submits are ordered on ctx->stream; make the stage streams see them.
+  MPC_CUDA(ctx, cudaEventRecord(ctx->ev_order, ctx->stream));
+  for (Stage& st : ctx->stage) MPC_CUDA(ctx, cudaStreamWaitEvent(st.stream, ctx->ev_order, 0));
+  ctx->last_timing_pending = false;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  const uint64_t L = (uint64_t)ctx->cfg.line_size;
+  cudaPointerAttributes attr;
+  bool pinned_src = false;
+  if (n_blocks && cudaPointerGetAttributes(&attr, h_lines) == cudaSuccess) pinned_src = (attr.type == cudaMemoryTypeHost);
+  cudaGetLastError();
+  uint64_t done_blocks = 0;
+  int which = 0;
+  while (done_blocks < n_blocks) {
+    Stage& st = ctx->stage[which];
+    rc = drain_stage(ctx, st);
+    if (rc != MPC_OK) return rc;
+    const uint64_t nb = (n_blocks - done_blocks < ctx->chunk_blocks) ? (n_blocks - done_blocks) : ctx->chunk_blocks;
+    const uint8_t* src = h_lines + done_blocks * L;
+    if (pinned_src) {
+      MPC_CUDA(ctx, cudaMemcpyAsync(st.d_lines, src, nb * L, cudaMemcpyHostToDevice, st.stream));
+    } else {
+      memcpy(st.h_pinned, src, nb * L);  // LoaderNPY.cpp:24-26 copied one line at a time; this is the chunked form
+      MPC_CUDA(ctx, cudaMemcpyAsync(st.d_lines, st.h_pinned, nb * L, cudaMemcpyHostToDevice, st.stream));
+    }
+    MPC_CUDA(ctx, cudaEventRecord(st.k_start, st.stream));
+    rc = launch(ctx, st.d_lines, nb, h_packed ? st.d_packed : nullptr, st.stream);
+    if (rc != MPC_OK) return rc;
+    MPC_CUDA(ctx, cudaEventRecord(st.k_stop, st.stream));
+    ctx->last_launches++;
+    if (h_packed) {
+      MPC_CUDA(ctx, cudaMemcpyAsync(st.h_packed, st.d_packed, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, st.stream));
+      st.user_packed = h_packed + done_blocks;
+      st.user_count = nb;
+    }
+    MPC_CUDA(ctx, cudaEventRecord(st.done, st.stream));
+    st.busy = true;
+    done_blocks += nb;
+    which ^= 1;
+  }
+  return MPC_OK;
+}
+
+int mpc_sync(mpc_ctx* ctx) {
+  if (!ctx) return MPC_E_ARG;
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (Stage& st : ctx->stage) {
+    int rc = drain_stage(ctx, st);
+    if (rc != MPC_OK) return rc;
+  }
+  MPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->last_timing_pending) {
+    MPC_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_start, ctx->ev_stop));
+    ctx->last_timing_pending = false;
+  }
+  return MPC_OK;
+}
+
+int mpc_stats_device_ptr(mpc_ctx* ctx, uint64_t** d_stats, size_t* n_words) {
+  if (!ctx || !d_stats || !n_words) return MPC_E_ARG;
+  *d_stats = ctx->d_stats;
+  *n_words = mpc::kStatsWords;
+  return MPC_OK;
+}
+
+int mpc_stats_expand(const mpc_config_pod* cfg, const uint64_t* w, size_t n_words, mpc_stats_pod* out) {
+  if (!cfg || !w || !out || n_words != mpc::kStatsWords) return MPC_E_ARG;
+  memset(out, 0, sizeof(*out));
+  const uint64_t line_bits = 8ull * (uint64_t)cfg->line_size;
+  for (int k = 0; k <= cfg->num_modules; k++) {
+    uint64_t cnt = 0, comp = 0;
+    for (int s = 0; s < MPC_HIST_BINS; s++) {
+      uint64_t h = w[mpc::kHistOff + (size_t)k * mpc::kHB + s];
+      out->hist[k][s] = h;
+      cnt += h;
+      comp += h * (uint64_t)s;
+    }
+    out->count[k] = cnt;           // ClusterStat::count, VPC.h:56
+    out->comp_bits[k] = comp;      // ClusterStat::compressedSize, VPC.h:54
+    out->res_abs[k] = w[mpc::kResAbsOff + k];
+    out->res_sq[k] = w[mpc::kResSqOff + k];
+    // lines that reached checkOtherPatterns: cluster -1 and every PredComp cluster (VPC.cpp:410-412)
+    out->res_lines[k] = (k == 0 || k - 1 >= cfg->first_predcomp) ? cnt : 0;
+    out->blocks += cnt;
+    out->compressed_bits += comp;  // CompResult::CompressedSize, CompResult.h:33
+  }
+  out->original_bits = out->blocks * line_bits;  // CompResult::OriginalSize, CompResult.h:32
+  return MPC_OK;
+}
+
+int mpc_finish(mpc_ctx* ctx, mpc_stats_pod* out) {
+  if (!ctx || !out) return MPC_E_ARG;
+  int rc = mpc_sync(ctx);
+  if (rc != MPC_OK) return rc;
+  std::vector<uint64_t> host(mpc::kStatsWords);
+  MPC_CUDA(ctx, cudaMemcpy(host.data(), ctx->d_stats, mpc::kStatsWords * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return mpc_stats_expand(&ctx->cfg, host.data(), host.size(), out);
+}
+
+int mpc_reset(mpc_ctx* ctx) {
+  if (!ctx) return MPC_E_ARG;
+  int rc = mpc_sync(ctx);
+  if (rc != MPC_OK) return rc;
+  MPC_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, mpc::kStatsWords * sizeof(uint64_t), ctx->stream));
+  MPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPC_OK;
+}
+
+int mpc_last_timing(mpc_ctx* ctx, float* kernel_ms, int* launches) {
+  if (!ctx) return MPC_E_ARG;
+  int rc = mpc_sync(ctx);
+  if (rc != MPC_OK) return rc;
+  if (kernel_ms) *kernel_ms = ctx->last_ms;
+  if (launches) *launches = ctx->last_launches;
+  return MPC_OK;
+}
+
+int mpc_synth_device(mpc_ctx* ctx, uint8_t* d_lines, uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,
+                     int kind, uint64_t seed) {
+  if (!ctx || (n_blocks && !d_lines)) return MPC_E_ARG;
+  if (kind < MPC_SYN_ZERO || kind > MPC_SYN_MIXED_REGIONS) return fail(ctx, MPC_E_ARG, "unknown synthetic kind %d", kind);
+  if (ctx->cfg.line_size != 128) return fail(ctx, MPC_E_ARG, "synthetic dumps are defined for 128-byte blocks");
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaError_t e = mpc::launch_synth(d_lines, first_block, n_blocks, total_blocks, kind, seed, ctx->stream);
+  if (e != cudaSuccess) return fail(ctx, MPC_E_CUDA, "synth launch failed: %s", cudaGetErrorString(e));
+  return MPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+// Device-side building blocks shared by the MPC kernels (sm_100a).
+//
+// Everything here is integer SWAR work on packed bytes / packed 16-bit scan rows.  The
+// functions are __host__ __device__ so that tests/ can compile this header with g++ and check
+// the bit tricks exhaustively on the CPU (tests/test_swar_host.py); on the device the
+// intrinsics map to PRMT / LOP3 / VIMNMX.U16x2 / VABSDIFF4 / IDP.4A.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MPC_HD __host__ __device__ __forceinline__
+#else
+#define MPC_HD static inline
+#endif
+
+namespace mpcdev {
+
+// ---- packed-halfword min (DPX on sm_90+/sm_100: VIMNMX.U16x2 / VIMNMX3.U16x2) -------------------
+MPC_HD uint32_t min_u16x2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __vminu2(a, b);
+#else
+  uint32_t lo = (a & 0xffffu) < (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu);
+  uint32_t hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+  return lo | (hi << 16);
+#endif
+}
+MPC_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __vimin3_u16x2(a, b, c);
+#else
+  return min_u16x2(min_u16x2(a, b), c);
+#endif
+}
+
+// ---- per-byte modular arithmetic on 4 packed bytes -----------------------------------------------
+// (a - b) mod 256 per byte.  ResidueModule::ProcessLine, ResidueModule.cpp:34.
+MPC_HD uint32_t sub_u8x4(uint32_t a, uint32_t b) {
+  const uint32_t H = 0x80808080u;
+  uint32_t t = (a | H) - (b & ~H);
+  return t ^ ((a ^ ~b) & H);
+}
+// (a + b) mod 256 per byte.  DiffBasePredictor::PredictLine, PredictorModule.cpp:104.
+MPC_HD uint32_t add_u8x4(uint32_t a, uint32_t b) {
+  const uint32_t H = 0x80808080u;
+  uint32_t t = (a & ~H) + (b & ~H);
+  return t ^ ((a ^ b) & H);
+}
+
+// ---- bit-plane XOR folded into the byte domain ------------------------------------------------------
+// BitplaneModule (plane b = bit 7-b of the residue byte, BitplaneModule.cpp:25-36) followed by
+// XORModule (XORModule.cpp:9-20).  `keep` has 0xff in every byte lane that must stay untouched
+// (column 0 of the residue line, XORModule.cpp:12 "j = 1").
+MPC_HD uint32_t xor_planes_consecutive(uint32_t r, uint32_t keep) {
+  return r ^ ((r >> 1) & 0x7f7f7f7fu & ~keep);
+}
+MPC_HD uint32_t xor_planes_first(uint32_t r, uint32_t keep) {
+  uint32_t msb = (r >> 7) & 0x01010101u & ~keep;
+  return r ^ (msb * 0x7fu);
+}
+
+// ---- common encoder on two packed scan rows -----------------------------------------------------------
+// A scan row is 16 bits; bit 15 holds scan position 0 (so the "front half" is the high byte).
+// w carries two rows (low / high halfword).  Returns, per halfword, the cost in bits of a
+// NON-ZERO row (FPCModule.cpp:47-66, costs FPCModule.h:55: single one 7, two consecutive ones 8,
+// front or back half zero 12, else 17) and 0 for an all-zero row; *nz gets 1 per non-zero row.
+MPC_HD uint32_t row2_cost(uint32_t w, uint32_t* nz_out) {
+  const uint32_t ONE = 0x00010001u;
+  uint32_t nz = min_u16x2(w, ONE);
+  uint32_t wz = w | (nz ^ ONE);       // zero rows become 0x0001 so that "- ONE" cannot borrow across
+  uint32_t t = wz - ONE;
+  uint32_t s = wz & t;                // row with its lowest set bit cleared: != 0 <=> two or more ones
+  uint32_t lb = wz & ~t;              // lowest set bit
+  uint32_t x = ((s >> 1) & 0x7fff7fffu) ^ lb;  // == 0 <=> exactly two ones, adjacent
+  uint32_t back = w & 0x00ff00ffu;
+  uint32_t front = (w >> 8) & 0x00ff00ffu;
+  uint32_t a = min3_u16x2(s, x, ONE);          // 1 <=> >= 2 ones and not "two consecutive"
+  uint32_t b3 = min3_u16x2(a, front, back);    // 1 <=> additionally both halves non-zero
+  uint32_t ns = min_u16x2(s, ONE);
+  *nz_out = nz;
+  return nz * 7u + ns + a * 4u + b3 * 5u;
+}
+
+// Cost of the zero rows of a block given the 64-bit mask of all-zero rows in scan order (bit i = row i,
+// only the low `rows` bits meaningful).  A maximal run of >= 2 zero rows costs 7, an isolated one 4
+// (FPCModule.cpp:27-45, 69-79).
+MPC_HD uint32_t zero_run_cost(uint64_t zmask) {
+  uint64_t start = zmask & ~(zmask << 1);
+  uint64_t single = start & ~(zmask >> 1);
+#if defined(__CUDA_ARCH__)
+  uint32_t ns = (uint32_t)__popcll(start), n1 = (uint32_t)__popcll(single);
+#else
+  uint32_t ns = (uint32_t)__builtin_popcountll(start), n1 = (uint32_t)__builtin_popcountll(single);
+#endif
+  return 7u * ns - 3u * n1;
+}
+
+// Number of leading all-zero rows (VPC.cpp:378-387); `rows` <= 64.
+MPC_HD uint32_t leading_zero_rows(uint64_t zmask, uint32_t rows) {
+  uint64_t nzm = ~zmask;
+  if (rows < 64) nzm |= ~0ull << rows;
+#if defined(__CUDA_ARCH__)
+  return nzm ? (uint32_t)(__ffsll((long long)nzm) - 1) : rows;
+#else
+  return nzm ? (uint32_t)__builtin_ctzll(nzm) : rows;
+#endif
+}
+
+// sum of the 4 bytes / sum of the squares of the 4 bytes (MAE / MSE numerators, ResidueModule.cpp:43-73)
+MPC_HD uint32_t sum_u8x4(uint32_t r) {
+#if defined(__CUDA_ARCH__)
+  return __vsadu4(r, 0u);
+#else
+  return (r & 0xff) + ((r >> 8) & 0xff) + ((r >> 16) & 0xff) + (r >> 24);
+#endif
+}
+MPC_HD uint32_t sumsq_u8x4(uint32_t r) {
+#if defined(__CUDA_ARCH__)
+  return __dp4a(r, r, 0u);
+#else
+  uint32_t s = 0;
+  for (int k = 0; k < 4; k++) { uint32_t b = (r >> (8 * k)) & 0xff; s += b * b; }
+  return s;
+#endif
+}
+
+// splitmix64 finaliser used by the synthetic dump generator (tools/gen_dump.py has the same function)
+MPC_HD uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+}  // namespace mpcdev

@@ -1,0 +1,25 @@
+// Registry of config-specialised kernels (thread-per-block mapping, tables folded at compile time).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mpc_capi.h"
+
+namespace mpc {
+
+struct SpecKernel {
+  const char* name;  // config name the kernel was instantiated for (e.g. "P6")
+  // true when `cfg` is exactly the config the kernel was compiled for
+  bool (*matches)(const mpc_config_pod& cfg);
+  cudaError_t (*launch)(const mpc_config_pod& cfg, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed,
+                        uint64_t* d_stats, int sm_count, cudaStream_t stream);
+};
+
+// defined in mpc_spec_list.cu
+extern const SpecKernel* const kSpecKernels[];
+extern const int kNumSpecKernels;
+
+// nullptr when no specialisation is linked in for this config
+const SpecKernel* find_spec_kernel(const mpc_config_pod& cfg);
+
+}  // namespace mpc

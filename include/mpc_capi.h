@@ -1,0 +1,161 @@
+/*
+ * mpc_capi.h -- C ABI of libmpc_b200.so, the B200 (sm_100a) implementation of the per-block
+ * compression loop of MPC (scalable-arch/CAL_22-MPC, where MPC is the `VPC` compressor).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The host
+ * classes in cal_22-mpc_b200/host/ (comp::Compressor / trace::Loader mirrors) and the Python
+ * ctypes binding sit above it.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference's src/).
+ *
+ * All functions return 0 on success and a negative MPC_E_* code on failure; the message is
+ * available from mpc_last_error() (per context) or mpc_global_error() (when no context exists).
+ * Nothing in the library aborts or exits.  There is NO CPU fallback: without a CUDA device
+ * mpc_create() fails with MPC_E_CUDA.
+ */
+#ifndef MPC_CAPI_H_
+#define MPC_CAPI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_MAX_LINE 128      /* bytes per block (cache line); supported: 32, 64, 128 */
+#define MPC_MAX_MODULES 16    /* overview.num_modules upper bound (clusters = modules + 1) */
+#define MPC_MAX_ENC_BITS 31   /* encoding bits per cluster must lie in [0, 31] */
+#define MPC_HIST_BINS (8 * MPC_MAX_LINE + 32) /* compressed size of a block is < MPC_HIST_BINS */
+
+enum { MPC_OK = 0, MPC_E_ARG = -1, MPC_E_CONFIG = -2, MPC_E_CUDA = -3, MPC_E_IO = -4, MPC_E_STATE = -5 };
+
+/* module kinds, VPC.cpp:126-325 */
+enum { MPC_MOD_ALLZERO = 0, MPC_MOD_ALLWORDSAME = 1, MPC_MOD_PREDCOMP = 2 };
+/* predictors, VPCmodules/PredictorModule.cpp */
+enum { MPC_PRED_ONE = 0, MPC_PRED_CONSEC = 1, MPC_PRED_DIFF = 2, MPC_PRED_WEIGHT = 3 };
+
+/* One PredComp module, flattened from the JSON the reference parses in VPC.cpp:131-306. */
+typedef struct {
+  int32_t kind;            /* MPC_MOD_* */
+  int32_t predictor;       /* MPC_PRED_* (PredComp only) */
+  int32_t root;            /* RootIndex */
+  int32_t consecutive_xor; /* XORModule.consecutiveXOR */
+  int32_t table_size;      /* ScanModule.TableSize, <= 8 * line_size */
+  uint8_t base[MPC_MAX_LINE];      /* BaseIndexTable (Diff/Weight) */
+  uint8_t diff[MPC_MAX_LINE];      /* (uint8_t)DiffTable[i]            (Diff)   */
+  int8_t shift[MPC_MAX_LINE];      /* (int)log2f(WeightTable[i])       (Weight) */
+  uint8_t scan_row[8 * MPC_MAX_LINE]; /* ScanModule.Rows (bit plane 0..7, 0 = MSB) */
+  uint8_t scan_col[8 * MPC_MAX_LINE]; /* ScanModule.Cols (byte column) */
+} mpc_module_pod;
+
+/* Whole config; replaces the object graph VPC::parseConfig builds (VPC.cpp:72-330). */
+typedef struct {
+  int32_t line_size;      /* overview.lineSize */
+  int32_t num_modules;    /* overview.num_modules */
+  int32_t has_wordsame;   /* module 1 is AllWordSame / ByteplaneAllSame */
+  int32_t first_predcomp; /* 1 or 2 */
+  int32_t enc_bits[MPC_MAX_MODULES + 1]; /* index = cluster + 1; cluster -1 = uncompressed */
+  mpc_module_pod modules[MPC_MAX_MODULES];
+} mpc_config_pod;
+
+/* Statistics of everything submitted since create/reset.  Replaces comp::VPCResult
+ * (VPC.h:34-238) + comp::CompResult (CompResult.h:24-86).  Cluster index k = selected + 1. */
+typedef struct {
+  uint64_t blocks;
+  uint64_t original_bits;   /* CompResult::OriginalSize   */
+  uint64_t compressed_bits; /* CompResult::CompressedSize */
+  uint64_t count[MPC_MAX_MODULES + 1];      /* ClusterStat::count           */
+  uint64_t comp_bits[MPC_MAX_MODULES + 1];  /* ClusterStat::compressedSize  */
+  uint64_t res_lines[MPC_MAX_MODULES + 1];  /* VPCResult::m_NumLines        */
+  uint64_t res_abs[MPC_MAX_MODULES + 1];    /* sum over lines of sum_i |r_i|  (MAE numerator) */
+  uint64_t res_sq[MPC_MAX_MODULES + 1];     /* sum over lines of sum_i r_i^2  (MSE numerator) */
+  uint64_t hist[MPC_MAX_MODULES + 1][MPC_HIST_BINS]; /* ClusterStat::compSizeHistogram */
+} mpc_stats_pod;
+
+/* number of uint64 words in the device-side statistics vector (the buffer an allreduce sums) */
+#define MPC_STATS_WORDS ((size_t)(2 * (MPC_MAX_MODULES + 1) + (MPC_MAX_MODULES + 1) * MPC_HIST_BINS))
+
+typedef struct mpc_ctx mpc_ctx;
+
+/* ---- config ---------------------------------------------------------------------------- */
+
+/* Parse + validate a reference-format JSON config (VPC::parseConfig, VPC.cpp:72-330).
+ * Configs the reference would run with undefined behaviour are rejected with MPC_E_CONFIG. */
+int mpc_config_from_json_file(const char* path, mpc_config_pod* out, char* err, size_t err_len);
+int mpc_config_from_json_text(const char* text, mpc_config_pod* out, char* err, size_t err_len);
+int mpc_config_validate(const mpc_config_pod* cfg, char* err, size_t err_len);
+
+/* ---- context --------------------------------------------------------------------------- */
+
+/* Replaces `new comp::VPC(configPath)` (main.cpp:88-91).  One context drives one GPU. */
+int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out);
+void mpc_destroy(mpc_ctx* ctx);
+const char* mpc_last_error(const mpc_ctx* ctx);
+const char* mpc_global_error(void);
+
+/* kernel selection: 0 = auto (specialised kernel when one exists for the config, else generic),
+ * 1 = generic warp-per-block kernel, 2 = specialised thread-per-block kernel (error if none). */
+int mpc_set_kernel(mpc_ctx* ctx, int which);
+/* name of the kernel the next submit will launch ("generic_warp", "spec_thread:<cfg>") */
+const char* mpc_kernel_name(const mpc_ctx* ctx);
+
+/* Run mpc_submit_device / mpc_synth_device / statistics resets on the caller's CUDA stream (a cudaStream_t
+ * passed as void*; NULL restores the context's own stream), so that the caller's events and collectives
+ * order against the kernels. */
+int mpc_set_stream(mpc_ctx* ctx, void* cuda_stream);
+
+/* ---- the hot path: replaces the compressLines loop (main.cpp:229-244) -------------------- */
+
+/* Blocks already resident in HBM.  d_lines: device pointer, 16-byte aligned, n_blocks*line_size
+ * bytes.  d_packed (optional, device): one uint16 per block = size_bits | (selected+1) << 11.
+ * Asynchronous on the context's stream; statistics accumulate on the device. */
+int mpc_submit_device(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed);
+
+/* Blocks in host memory (pageable or pinned).  Chunked, double-buffered: pinned staging ->
+ * cudaMemcpyAsync H2D on alternating streams overlapped with the kernel.  h_packed (optional,
+ * host) receives the per-block results.  Returns after the last chunk has been issued;
+ * mpc_finish() / mpc_sync() wait for completion. */
+int mpc_submit_host(mpc_ctx* ctx, const uint8_t* h_lines, uint64_t n_blocks, uint16_t* h_packed);
+
+/* Wait for all submitted work. */
+int mpc_sync(mpc_ctx* ctx);
+
+/* Device statistics vector (MPC_STATS_WORDS uint64, layout private to the library but linear:
+ * element-wise sums of vectors from several GPUs are valid).  This is the buffer a multi-GPU
+ * caller all-reduces (ncclAllReduce, ncclUint64/ncclInt64, ncclSum) before mpc_finish(). */
+int mpc_stats_device_ptr(mpc_ctx* ctx, uint64_t** d_stats, size_t* n_words);
+
+/* Sync, copy the statistics vector back and expand it.  Replaces compressor->GetResult()
+ * (Compressor.h:29, main.cpp:246). */
+int mpc_finish(mpc_ctx* ctx, mpc_stats_pod* out);
+
+/* Expand a host copy of a statistics vector (e.g. after an allreduce done elsewhere). */
+int mpc_stats_expand(const mpc_config_pod* cfg, const uint64_t* words, size_t n_words, mpc_stats_pod* out);
+
+/* Zero the device statistics (new file / new run). */
+int mpc_reset(mpc_ctx* ctx);
+
+/* Device time (CUDA events on the context's stream) of the kernels launched by the most recent
+ * mpc_submit_device / mpc_submit_host call, and the number of kernel launches it made. */
+int mpc_last_timing(mpc_ctx* ctx, float* kernel_ms, int* launches);
+
+/* ---- synthetic dumps (BASELINE.json configs; generator shared with tools/gen_dump.py) ---- */
+
+enum {
+  MPC_SYN_ZERO = 0, MPC_SYN_WORDSAME = 1, MPC_SYN_SMOOTH_F32 = 2, MPC_SYN_RAMP_I32 = 3,
+  MPC_SYN_POINTER = 4, MPC_SYN_RANDOM = 5, MPC_SYN_SPARSE_I32 = 6, MPC_SYN_NOISY_F32 = 7,
+  MPC_SYN_MIXED_HASHED = 8, /* class = hash(seed, block) % 8 */
+  MPC_SYN_MIXED_REGIONS = 9 /* class = block * 8 / total_blocks */
+};
+/* Fill d_lines (device, 128-byte blocks) with blocks [first_block, first_block + n_blocks) of the
+ * synthetic dump `kind` with `seed`; total_blocks is the size of the whole (possibly sharded) dump. */
+int mpc_synth_device(mpc_ctx* ctx, uint8_t* d_lines, uint64_t first_block, uint64_t n_blocks,
+                     uint64_t total_blocks, int kind, uint64_t seed);
+
+/* ---- library info ---------------------------------------------------------------------- */
+const char* mpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_CAPI_H_ */

@@ -1,0 +1,166 @@
+"""GPU parity proper: the CUDA path, called through the C ABI (include/mpc_capi.h), against the CPU oracle and
+the committed reference goldens.  Bit-exact: same selected cluster and same compressed bit count per block,
+same totals, histograms and MAE/MSE numerators."""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import SHIPPED, cfg_path, random_blocks, random_config
+from oracle.bridge import OracleMPC
+from tools.gen_dump import KINDS, kat_blocks, synth
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [1, 0]  # 1 = generic warp-per-block; 0 = auto (specialised when built in)
+
+
+def check_against_oracle(mpcb, m, oracle, blocks):
+    sizes, sels, st = m.compress(blocks)
+    r = oracle.run(blocks)
+    bad = np.nonzero((sizes != r.sizes) | (sels != r.sels))[0]
+    assert bad.size == 0, f"{bad.size} blocks differ, first {bad[:5]}: gpu {sizes[bad[:5]]}/{sels[bad[:5]]} " \
+                          f"oracle {r.sizes[bad[:5]]}/{r.sels[bad[:5]]} kernel {m.kernel_name()}"
+    assert st.blocks == r.blocks and st.OriginalSize == r.OriginalSize and st.CompressedSize == r.CompressedSize
+    assert np.array_equal(st.count, r.count) and np.array_equal(st.comp_bits, r.comp_bits)
+    assert np.array_equal(st.res_lines, r.res_lines)
+    assert np.array_equal(st.res_abs, r.res_abs) and np.array_equal(st.res_sq, r.res_sq)
+    hb = r.hist.shape[1]
+    assert np.array_equal(st.hist[:, :hb], r.hist) and not st.hist[:, hb:].any()
+    return st
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_known_answers(mpcb, kernel):
+    m = mpcb.Mpc(cfg_path("P6"))
+    m.set_kernel(kernel)
+    sizes, sels, st = m.compress(kat_blocks())
+    assert sizes.tolist() == [3, 35, 146, 1027, 1027, 1027, 201, 263, 35]
+    assert sels.tolist() == [0, 1, 4, -1, -1, -1, 5, 3, 1]
+    assert st.OriginalSize == 9 * 1024
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("cfg", SHIPPED)
+def test_reference_golden(mpcb, golden, cfg, kernel):
+    m = mpcb.Mpc(cfg_path(cfg))
+    m.set_kernel(kernel)
+    sizes, sels, st = m.compress(golden["blocks"])
+    assert np.array_equal(sizes, golden[f"{cfg}_sizes"].astype(np.uint32))
+    assert np.array_equal(sels, golden[f"{cfg}_sels"].astype(np.int32))
+    orig, comp = (int(v) for v in golden[f"{cfg}_totals"])
+    assert (st.OriginalSize, st.CompressedSize) == (orig, comp)
+    assert st.CompRatio == float(golden[f"{cfg}_ratio"][0])
+    stat, fl = golden[f"{cfg}_stat"], golden[f"{cfg}_fl"]
+    assert np.array_equal(st.count, stat[:, 0]) and np.array_equal(st.comp_bits, stat[:, 2])
+    for k in range(st.count.size):
+        assert st.mae(k) == fl[k, 1] and st.mse(k) == fl[k, 2]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("cfg", SHIPPED)
+@pytest.mark.parametrize("kind", KINDS)
+def test_synthetic_classes(mpcb, cfg, kind, kernel):
+    m = mpcb.Mpc(cfg_path(cfg))
+    m.set_kernel(kernel)
+    blocks = synth(kind, 4242, 12345, 3001, 1 << 20)  # ragged count on purpose
+    check_against_oracle(mpcb, m, OracleMPC(cfg_path(cfg)), blocks)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_configs(mpcb, seed):
+    rng = np.random.default_rng(7000 + seed)
+    L = int(rng.choice([32, 64, 128]))
+    cfg = random_config(rng, L=L)
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(cfg)))
+    check_against_oracle(mpcb, m, OracleMPC(cfg), random_blocks(rng, 777, L))
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 255, 257])
+def test_ragged_counts(mpcb, n):
+    m = mpcb.Mpc(cfg_path("P6"))
+    blocks = synth("mixed_hashed", 1, 0, n, max(n, 1))
+    sizes, sels, st = m.compress(blocks)
+    r = OracleMPC(cfg_path("P6")).run(blocks) if n else None
+    assert st.blocks == n
+    if n:
+        assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
+    else:
+        assert st.CompressedSize == 0 and st.OriginalSize == 0
+
+
+def test_statistics_accumulate_and_reset(mpcb):
+    m = mpcb.Mpc(cfg_path("F4"))
+    a = synth("mixed_hashed", 3, 0, 1000, 2000)
+    b = synth("mixed_hashed", 3, 1000, 1000, 2000)
+    m.reset()
+    m.submit_host(a)
+    m.submit_host(b)
+    st = m.finish()
+    r = OracleMPC(cfg_path("F4")).run(np.concatenate([a, b]))
+    assert st.blocks == 2000 and st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count)
+    m.reset()
+    assert m.finish().blocks == 0
+
+
+def test_device_submit_and_synth_match_numpy(mpcb):
+    import torch
+    m = mpcb.Mpc(cfg_path("P6"))
+    n, total, first = 5000, 1 << 22, 777777
+    for kind in KINDS:
+        d = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+        m.synth_device(d.data_ptr(), first, n, total, kind, 99)
+        m.sync()
+        assert np.array_equal(d.cpu().numpy().reshape(n, 128), synth(kind, 99, first, n, total)), kind
+    blocks = synth("mixed_hashed", 99, first, n, total)
+    d = torch.from_numpy(blocks).cuda()
+    packed = torch.zeros(n, dtype=torch.int16, device="cuda")
+    m.reset()
+    m.submit_device(d.data_ptr(), n, packed.data_ptr())
+    st = m.finish()
+    sizes, sels = mpcb.unpack(packed.cpu().numpy().view(np.uint16))
+    r = OracleMPC(cfg_path("P6")).run(blocks)
+    assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels) and st.CompressedSize == r.CompressedSize
+    ms, launches = m.last_timing()
+    assert launches == 1 and ms > 0
+
+
+def test_chunked_host_path_multiple_chunks(mpcb):
+    # > 2 chunks of 64 MiB so that both staging buffers are reused (LoaderNPY replacement path)
+    m = mpcb.Mpc(cfg_path("F4"))
+    n = (160 << 20) // 128
+    blocks = synth("mixed_regions", 5, 0, n, n)
+    sizes, sels, st = m.compress(blocks)
+    r = OracleMPC(cfg_path("F4")).run(blocks)
+    assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
+    assert st.CompressedSize == r.CompressedSize and np.array_equal(st.hist[:, :r.hist.shape[1]], r.hist)
+
+
+@pytest.mark.parametrize("cfg,kind", [("F4", "smooth_f32"), ("P6", "mixed_hashed")])
+def test_full_size_properties(mpcb, cfg, kind):
+    """BASELINE sizes (1 GiB): size-independent properties instead of a CPU run of the whole dump --
+    (1) per-block results of a seeded window equal the oracle, (2) totals equal the sum of the per-block
+    results, (3) two half submissions accumulate to the same statistics as one (linearity)."""
+    import torch
+    m = mpcb.Mpc(cfg_path(cfg))
+    n = (1 << 30) // 128
+    d = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    packed = torch.zeros(n, dtype=torch.int16, device="cuda")
+    m.synth_device(d.data_ptr(), 0, n, n, kind, 2024)
+    m.reset()
+    m.submit_device(d.data_ptr(), n, packed.data_ptr())
+    st = m.finish()
+    sizes, sels = mpcb.unpack(packed.cpu().numpy().view(np.uint16))
+    assert st.blocks == n and st.OriginalSize == n * 1024
+    assert st.CompressedSize == int(sizes.astype(np.uint64).sum())
+    assert np.array_equal(st.count, np.bincount(sels + 1, minlength=st.count.size).astype(np.uint64))
+    w0, wn = 3_000_000, 20000
+    r = OracleMPC(cfg_path(cfg)).run(synth(kind, 2024, w0, wn, n))
+    assert np.array_equal(sizes[w0:w0 + wn], r.sizes) and np.array_equal(sels[w0:w0 + wn], r.sels)
+    m.reset()
+    half = n // 2
+    m.submit_device(d.data_ptr(), half, None)
+    m.submit_device(d.data_ptr() + half * 128, n - half, None)
+    st2 = m.finish()
+    assert st2.CompressedSize == st.CompressedSize and np.array_equal(st2.hist, st.hist)
+    assert np.array_equal(st2.res_abs, st.res_abs) and np.array_equal(st2.res_sq, st.res_sq)

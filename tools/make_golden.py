@@ -1,0 +1,109 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ from the UNMODIFIED reference (oracle/_ref, built by oracle/build_ref.sh from
+/root/reference).  Run in the build container only -- the GPU box has no /root/reference, it uses the
+committed fixtures.
+
+  tests/golden/mpc_blocks.npz    640 blocks (9 known-answer blocks of SURVEY.md section 8c, 8 synthetic classes,
+                                 hand-made edge blocks); per shipped config: per-block size + selected
+                                 cluster, totals, per-cluster stats, MAE/MSE doubles, histograms -- all
+                                 produced by comp::VPC::CompressLine / VPCResult of the reference.
+  tests/golden/cli_<cfg>_*.csv   the two CSV files the reference CLI appends for a 200-row .npy (run twice, so
+                                 header + 2 rows), plus its stdout line.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.bridge import REF_BIN, RefCompressor  # noqa: E402
+from tools.gen_dump import kat_blocks, synth  # noqa: E402
+
+CONFIGS = ["P6", "F4", "Z1", "E5"]
+
+
+def edge_blocks():
+    rng = np.random.default_rng(99)
+    out = []
+    for pos in (0, 1, 3, 4, 64, 127):  # a single non-zero byte
+        b = np.zeros(128, np.uint8)
+        b[pos] = 1 + pos
+        out.append(b)
+    for v in (1, 0x80, 0xFF):  # all bytes equal
+        out.append(np.full(128, v, np.uint8))
+    b = np.tile(np.array([1, 2, 3, 4], np.uint8), 32)  # word-same, then broken in the last byte
+    out.append(b.copy())
+    b[127] ^= 1
+    out.append(b.copy())
+    b = np.tile(np.array([1, 2, 3, 4], np.uint8), 32)
+    b[4] ^= 0x10
+    out.append(b)
+    for step in (1, 2, 3, 255):  # byte ramps
+        out.append((np.arange(128) * step).astype(np.uint8))
+    for dt in (np.int16, np.int32, np.int64):  # slow integer ramps
+        out.append((1000 + np.arange(128 // np.dtype(dt).itemsize)).astype(dt).view(np.uint8))
+    out.append(np.linspace(-1, 1, 32, dtype=np.float32).view(np.uint8))
+    out.append(np.linspace(100, 101, 16, dtype=np.float64).view(np.uint8))
+    for k in range(12):  # sparse bit patterns: few ones, to reach the cheap row patterns
+        b = np.zeros(128, np.uint8)
+        idx = rng.integers(0, 128, size=k + 1)
+        b[idx] = (1 << rng.integers(0, 8, size=k + 1)).astype(np.uint8)
+        out.append(b)
+    return np.stack(out)
+
+
+def golden_blocks():
+    parts = [kat_blocks(), edge_blocks()]
+    for kind in range(8):
+        parts.append(synth(kind, 20221, 1000 * kind, 72, 1 << 20))
+    blocks = np.concatenate(parts)
+    assert blocks.shape[0] <= 640
+    pad = synth("mixed_hashed", 5, 0, 640 - blocks.shape[0], 640)
+    return np.concatenate([blocks, pad])
+
+
+def main():
+    gold = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+    blocks = golden_blocks()
+    data = {"blocks": blocks}
+    for cfg in CONFIGS:
+        path = os.path.join(ROOT, "configs", cfg + ".json")
+        ref = RefCompressor("VPC", path)
+        sizes, sels = ref.compress(blocks)
+        orig, comp, ratio = ref.totals()
+        stat, fl, hist = ref.vpc_stats()
+        data.update({f"{cfg}_sizes": sizes.astype(np.uint16), f"{cfg}_sels": sels.astype(np.int8),
+                     f"{cfg}_totals": np.array([orig, comp], np.uint64), f"{cfg}_ratio": np.array([ratio]),
+                     f"{cfg}_stat": stat, f"{cfg}_fl": fl,
+                     f"{cfg}_hist_nz": np.argwhere(hist), f"{cfg}_hist_val": hist[hist != 0]})
+        print(cfg, "ratio", ratio, "clusters", stat[:, 0].tolist())
+    np.savez_compressed(os.path.join(gold, "mpc_blocks.npz"), **data)
+    # CLI goldens: <tmp>/ds/golden_set.npy -> workload name "ds_golden_set" (main.cpp:142-157)
+    with tempfile.TemporaryDirectory() as tmp:
+        ds = os.path.join(tmp, "ds")
+        os.makedirs(ds)
+        np.save(os.path.join(ds, "golden_set.npy"), np.concatenate([blocks[:199], np.zeros((1, 128), np.uint8)]))
+        for cfg in ("P6", "F4"):
+            outdir = os.path.join(tmp, "out_" + cfg)
+            os.makedirs(outdir)
+            cfgpath = os.path.join(ROOT, "configs", cfg + ".json")
+            stdout = ""
+            for _ in range(2):
+                r = subprocess.run([REF_BIN, "-a", "VPC", "-i", os.path.join(ds, "golden_set.npy"), "-c", cfgpath,
+                                    "-o", outdir], capture_output=True, text=True, check=True)
+                stdout = r.stdout
+            for suffix in ("results.csv", "results_detail.csv"):
+                with open(os.path.join(outdir, f"{cfg}_{suffix}")) as f, \
+                        open(os.path.join(gold, f"cli_{cfg}_{suffix}"), "w") as g:
+                    g.write(f.read())
+            with open(os.path.join(gold, f"cli_{cfg}_stdout.txt"), "w") as g:
+                g.write(stdout)
+            print(cfg, "cli:", stdout.strip())
+
+
+if __name__ == "__main__":
+    main()
