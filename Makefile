@@ -10,11 +10,22 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -I$(CSRC
 CXXFLAGS := -O3 -std=c++17 -fPIC -Iinclude -I$(CSRC) -Wall
 
 LIB      := $(PKG)/libmpc_b200.so
-CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu
+SPEC_CFGS := P6 F4 Z1 E5
+SPEC_SRCS := $(foreach c,$(SPEC_CFGS),$(CSRC)/spec/spec_$(c).cu)
+CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu $(SPEC_SRCS)
 CU_OBJS  := $(CU_SRCS:.cu=.o)
 CC_OBJS  := $(CSRC)/mpc_config.o
 
 all: $(LIB) compressor oracle
+
+# config compiler: one specialised schedule per shipped config (generated sources are committed)
+$(SPEC_SRCS) $(CSRC)/spec/spec_list.inc &: tools/gen_spec.py $(foreach c,$(SPEC_CFGS),configs/$(c).json)
+	python tools/gen_spec.py $(foreach c,$(SPEC_CFGS),configs/$(c).json)
+
+$(CSRC)/mpc_spec_list.o: $(CSRC)/spec/spec_list.inc
+
+$(CSRC)/spec/%.o: $(CSRC)/spec/%.cu $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(@:.o=.ptxas.txt) || (cat $(@:.o=.ptxas.txt); false)
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -38,7 +49,7 @@ sass: $(LIB)
 	cuobjdump -sass $(LIB) > profiles/libmpc_b200.sass
 
 clean:
-	rm -f $(CSRC)/*.o $(LIB) bin/compressor
+	rm -f $(CSRC)/*.o $(CSRC)/spec/*.o $(LIB) bin/compressor
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean sass

@@ -208,7 +208,8 @@ def run_ours(a):
     m = mpcb.Mpc(cfg_path, device=local)
     if a.kernel is not None:
         m.set_kernel(a.kernel)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # not the legacy default stream: its handle is 0, which the ABI reads as "own stream"
+    torch.cuda.set_stream(stream)
     m.set_stream(stream.cuda_stream)
 
     n = a.bytes_per_gpu // BLOCK

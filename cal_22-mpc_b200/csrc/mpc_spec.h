@@ -15,6 +15,9 @@ struct SpecKernel {
                         uint64_t* d_stats, int sm_count, cudaStream_t stream);
 };
 
+// true when the two configs describe the same computation (fields the kernels depend on)
+bool spec_pod_equal(const mpc_config_pod& a, const mpc_config_pod& b);
+
 // defined in mpc_spec_list.cu
 extern const SpecKernel* const kSpecKernels[];
 extern const int kNumSpecKernels;

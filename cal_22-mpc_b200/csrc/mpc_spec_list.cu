@@ -1,7 +1,14 @@
-// List of specialised kernels linked into the library (none yet: the generic kernel serves all configs).
+// Specialised kernels linked into the library (spec/spec_list.inc is written by tools/gen_spec.py).
 #include "mpc_spec.h"
 
 namespace mpc {
-const SpecKernel* const kSpecKernels[] = {nullptr};
-const int kNumSpecKernels = 0;
+#define MPC_SPEC(n) extern const SpecKernel kSpec_##n;
+#include "spec/spec_list.inc"
+#undef MPC_SPEC
+const SpecKernel* const kSpecKernels[] = {
+#define MPC_SPEC(n) &kSpec_##n,
+#include "spec/spec_list.inc"
+#undef MPC_SPEC
+    nullptr};
+const int kNumSpecKernels = (int)(sizeof(kSpecKernels) / sizeof(kSpecKernels[0])) - 1;
 }  // namespace mpc

@@ -164,3 +164,21 @@ def test_full_size_properties(mpcb, cfg, kind):
     st2 = m.finish()
     assert st2.CompressedSize == st.CompressedSize and np.array_equal(st2.hist, st.hist)
     assert np.array_equal(st2.res_abs, st.res_abs) and np.array_equal(st2.res_sq, st.res_sq)
+
+
+@pytest.mark.parametrize("cfg", SHIPPED)
+def test_shipped_configs_use_the_specialised_kernel(mpcb, cfg):
+    m = mpcb.Mpc(cfg_path(cfg))
+    assert m.kernel_name() == "spec_thread:" + cfg
+    m.set_kernel(1)
+    assert m.kernel_name() == "generic_warp"
+    m.set_kernel(2)
+    assert m.kernel_name() == "spec_thread:" + cfg
+
+
+def test_unknown_config_falls_back_to_generic_and_says_so(mpcb):
+    rng = np.random.default_rng(5)
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(random_config(rng, L=64, n_pred=2))))
+    assert m.kernel_name() == "generic_warp"
+    with pytest.raises(mpcb.MpcError):
+        m.set_kernel(2)
