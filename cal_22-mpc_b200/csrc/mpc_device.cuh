@@ -33,6 +33,17 @@ MPC_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
 #endif
 }
 
+// packed-halfword add, wrapping per halfword (PTX add.u16x2 -> VIADD.U16x2 on sm_90+/sm_100)
+MPC_HD uint32_t add_u16x2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("add.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+#else
+  return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
+#endif
+}
+
 // ---- per-byte modular arithmetic on 4 packed bytes -----------------------------------------------
 // (a - b) mod 256 per byte.  ResidueModule::ProcessLine, ResidueModule.cpp:34.
 MPC_HD uint32_t sub_u8x4(uint32_t a, uint32_t b) {
@@ -67,11 +78,10 @@ MPC_HD uint32_t xor_planes_first(uint32_t r, uint32_t keep) {
 MPC_HD uint32_t row2_cost(uint32_t w, uint32_t* nz_out) {
   const uint32_t ONE = 0x00010001u;
   uint32_t nz = min_u16x2(w, ONE);
-  uint32_t wz = w | (nz ^ ONE);       // zero rows become 0x0001 so that "- ONE" cannot borrow across
-  uint32_t t = wz - ONE;
-  uint32_t s = wz & t;                // row with its lowest set bit cleared: != 0 <=> two or more ones
-  uint32_t lb = wz & ~t;              // lowest set bit
-  uint32_t x = ((s >> 1) & 0x7fff7fffu) ^ lb;  // == 0 <=> exactly two ones, adjacent
+  uint32_t t = add_u16x2(w, 0xffffffffu);  // row - 1 per halfword (no borrow across the halves)
+  uint32_t s = w & t;                 // row with its lowest set bit cleared: != 0 <=> two or more ones
+  uint32_t lb = w & ~t;               // lowest set bit (0 for a zero row)
+  uint32_t x = ((s >> 1) & 0x7fff7fffu) ^ lb;  // == 0 <=> exactly two ones, adjacent (or fewer than two ones)
   uint32_t back = w & 0x00ff00ffu;
   uint32_t front = (w >> 8) & 0x00ff00ffu;
   uint32_t a = min3_u16x2(s, x, ONE);          // 1 <=> >= 2 ones and not "two consecutive"

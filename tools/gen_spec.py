@@ -205,6 +205,16 @@ class Module:
             e = f"(({e} & 0xffffff00u) | {rootbyte})"
         return f"const uint32_t {name} = {e};"
 
+    def eq_expr(self, w):
+        """line word ^ predicted word for residue word w; a zero byte <=> that residue byte is zero."""
+        xe = gather_expr("x", self.xsrc[4 * w:4 * w + 4])
+        e = f"({xe} ^ {self.pred_expr(w)})"
+        if w == 0:  # residue position 0 is the root byte itself (ResidueModule.cpp:26-27)
+            rw, rb = self.root // 4, self.root % 4
+            rootbyte = f"(x[{rw}] & 0xffu)" if rb == 0 else f"((x[{rw}] >> {8 * rb}) & 0xffu)"
+            e = f"(({e} & 0xffffff00u) | {rootbyte})"
+        return e
+
     def g_from_r(self, w, r):
         if self.cxor:
             return f"xc({r}, 0x{0x7f7f7f00 if w == 0 else 0x7f7f7f7f:08x}u)"
@@ -248,27 +258,43 @@ def emit_full(m, out):
 
 
 def emit_score_cm(m, out):
+    """Leading zero rows of a column-major module.  A scan row is two bytes of the XOR-ed residue line, and such
+    a byte is zero exactly when the line byte equals its prediction (both XOR variants map 0 -> 0 only), so the
+    score needs no subtraction: e<w> = line word ^ predicted word, tested under the byte masks of the row."""
     out.append(f"__device__ __forceinline__ uint32_t score_{m.idx}(const uint32_t (&x)[32]) {{")
     have = set()
-    nrows = 64
     cols = m.cols + [None] * (L - len(m.cols))
-    for k in range(nrows):
-        a, b = cols[2 * k], cols[2 * k + 1]
+    tests = []
+    for k in range(64):
         need = {}
-        for cidx in (a, b):
+        for cidx in (cols[2 * k], cols[2 * k + 1]):
             if cidx is None:
                 continue
             need.setdefault(cidx // 4, 0)
             need[cidx // 4] |= 0xFF << (8 * (cidx % 4))
-        if not need:
-            continue  # row of zeros by construction (table shorter than the array)
-        for w in sorted(need):
-            if w not in have:
-                out.append("  " + m.residue_stmts(w, f"r{w}"))
-                out.append(f"  const uint32_t g{w} = {m.g_from_r(w, f'r{w}')};")
-                have.add(w)
-        terms = [f"(g{w} & 0x{mask:08x}u)" if mask != 0xFFFFFFFF else f"g{w}" for w, mask in sorted(need.items())]
-        out.append(f"  if (({' | '.join(terms)}) != 0u) return {k}u;")
+        tests.append(need)
+    k = 0
+    while k < 64:
+        group = [kk for kk in (k, k + 1) if kk < 64 and tests[kk]]
+        for kk in group:
+            for w in sorted(tests[kk]):
+                if w not in have:
+                    out.append(f"  const uint32_t e{w} = {m.eq_expr(w)};")
+                    have.add(w)
+        exprs = []
+        for kk in group:
+            terms = {}
+            for w, mask in sorted(tests[kk].items()):
+                terms.setdefault(mask, []).append(f"e{w}")
+            parts = [f"(({' | '.join(ws)}) & 0x{mask:08x}u)" if mask != 0xFFFFFFFF else f"({' | '.join(ws)})"
+                     for mask, ws in terms.items()]
+            exprs.append((kk, " | ".join(parts)))
+        if len(exprs) == 2:
+            (k0, e0), (k1, e1) = exprs
+            out.append(f"  {{ const uint32_t t0 = {e0}, t1 = {e1}; if ((t0 | t1) != 0u) return t0 ? {k0}u : {k1}u; }}")
+        elif len(exprs) == 1:
+            out.append(f"  if (({exprs[0][1]}) != 0u) return {exprs[0][0]}u;")
+        k += 2
     out.append("  return 64u;")
     out.append("}")
 
@@ -301,8 +327,12 @@ def emit_score_pm(m, out):
             out.append(f"      if (({chunk_or(j, 'g')}) & 0x80808080u) return {j}u;")
         out.append("    }")
         out.append("  }")
-    for w in range(W):
-        out.append(f"  g[{w}] = {m.g_from_r(w, f'g[{w}]')};")
+    if m.rho != list(range(8)):
+        for w in range(W):
+            out.append(f"  g[{w}] = {m.g_from_r(w, f'g[{w}]')};")
+    else:
+        out.append("  // planes are scanned MSB first: while every higher plane is zero, plane b of the XOR-ed residue equals")
+        out.append("  // plane b of the residue itself (XORModule.cpp:9-20), so the leading-zero count needs no XOR stage")
     out.append("  uint32_t f[8];")
     for j in range(8):
         out.append(f"  {{ uint32_t o = {chunk_or(j, 'g')}; o |= o >> 16; o |= o >> 8; f[{j}] = {plane_order_expr('o', m.rho)}; }}")
