@@ -19,8 +19,10 @@ CC_OBJS  := $(CSRC)/mpc_config.o
 all: $(LIB) compressor oracle
 
 # config compiler: one specialised schedule per shipped config (generated sources are committed)
-$(SPEC_SRCS) $(CSRC)/spec/spec_list.inc &: tools/gen_spec.py $(foreach c,$(SPEC_CFGS),configs/$(c).json)
+$(CSRC)/spec/.stamp: tools/gen_spec.py $(foreach c,$(SPEC_CFGS),configs/$(c).json)
 	python tools/gen_spec.py $(foreach c,$(SPEC_CFGS),configs/$(c).json)
+	@touch $@
+$(SPEC_SRCS) $(CSRC)/spec/spec_list.inc: $(CSRC)/spec/.stamp
 
 $(CSRC)/mpc_spec_list.o: $(CSRC)/spec/spec_list.inc
 
@@ -37,9 +39,11 @@ $(LIB): $(CU_OBJS) $(CC_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -Xlinker --no-undefined
 
 HOST_SRCS := $(wildcard $(HOST)/*.cpp $(HOST)/compressor/*.cpp $(HOST)/loader/*.cpp)
-compressor: $(HOST_SRCS) $(wildcard $(HOST)/*.h $(HOST)/compressor/*.h $(HOST)/loader/*.h) $(LIB)
-	@if [ -n "$(HOST_SRCS)" ]; then \
-	  $(CXX) $(CXXFLAGS) -I$(HOST) $(HOST_SRCS) -o bin/compressor -L$(PKG) -lmpc_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lpthread; \
+compressor: bin/compressor
+bin/compressor: $(HOST_SRCS) $(wildcard $(HOST)/*.h $(HOST)/compressor/*.h $(HOST)/loader/*.h) $(LIB)
+	@mkdir -p bin; if [ -n "$(HOST_SRCS)" ]; then \
+	  $(CXX) $(CXXFLAGS) -I$(HOST) -I/usr/local/cuda/include $(HOST_SRCS) -o bin/compressor -L$(PKG) -lmpc_b200 \
+	    -L/usr/local/cuda/lib64 -lcudart -lnccl -Wl,-rpath,'$$ORIGIN/../$(PKG)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread; \
 	fi
 
 oracle:
@@ -52,4 +56,4 @@ clean:
 	rm -f $(CSRC)/*.o $(CSRC)/spec/*.o $(LIB) bin/compressor
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean sass
+.PHONY: all oracle clean sass compressor

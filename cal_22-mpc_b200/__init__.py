@@ -9,5 +9,7 @@ used by the tests and bench.py.  Import with importlib (the directory name has a
 from .capi import (ConfigPod, ModulePod, Mpc, MpcError, Stats, StatsPod, SYN, LIB_PATH, SYMBOLS, lib, load_config,
                    unpack)
 
-__all__ = ["ConfigPod", "ModulePod", "Mpc", "MpcError", "Stats", "StatsPod", "SYN", "LIB_PATH", "SYMBOLS", "lib",
+from .shard import allreduce_stats, shard_range
+
+__all__ = ["allreduce_stats", "shard_range", "ConfigPod", "ModulePod", "Mpc", "MpcError", "Stats", "StatsPod", "SYN", "LIB_PATH", "SYMBOLS", "lib",
            "load_config", "unpack"]

@@ -1,0 +1,91 @@
+"""Exhaustive CPU checks of the bit tricks the kernels are built from (csrc/mpc_device.cuh compiled with g++)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+
+
+@pytest.fixture(scope="module")
+def swar(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("swar") / "libswar.so")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "cal_22-mpc_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "swar_host.cpp"), "-o", so], check=True)
+    l = ctypes.CDLL(so)
+    l.t_zero_run_cost.argtypes = [ctypes.c_ulonglong]
+    l.t_lzr.argtypes = [ctypes.c_ulonglong, ctypes.c_uint]
+    for name in ("t_sub", "t_add", "t_xc", "t_xf", "t_zero_run_cost", "t_lzr", "t_row2_cost"):
+        getattr(l, name).restype = ctypes.c_uint
+    return l
+
+
+def row_cost_reference(v):
+    """FPCModule.cpp:47-66 on a 16-bit row whose bit 15 is scan position 0."""
+    bits = [(v >> (15 - k)) & 1 for k in range(16)]
+    ones = [k for k in range(16) if bits[k]]
+    if not ones:
+        return 0
+    if len(ones) == 1:
+        return 7
+    if len(ones) == 2 and ones[1] - ones[0] == 1:
+        return 8
+    if not any(bits[:8]) or not any(bits[8:]):
+        return 12
+    return 17
+
+
+def test_row_cost_exhaustive(swar):
+    want = np.array([row_cost_reference(v) for v in range(65536)], dtype=np.uint32)
+    lo = np.zeros(65536, np.uint32)
+    hi = np.zeros(65536, np.uint32)
+    for other in (0x0000, 0xFFFF, 0x0001, 0x8000, 0x8001, 0x0180, 0x5A5A):
+        swar.t_row_costs(other, lo.ctypes.data, hi.ctypes.data)
+        for arr in (lo, hi):
+            assert np.array_equal(arr & 0x7FFFFFFF, want), hex(other)
+            assert np.array_equal(arr >> 31, (np.arange(65536) != 0).astype(np.uint32)), hex(other)
+
+
+def test_bytewise_add_sub_xor(swar):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 2**32, 20000, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2**32, 20000, dtype=np.uint64).astype(np.uint32)
+    a[:8] = [0, 0xFFFFFFFF, 0x80808080, 0x7F7F7F7F, 0x00FF00FF, 0x01010101, 0xFF00FF00, 0x80000000]
+    b[:8] = [0xFFFFFFFF, 0, 0x01010101, 0x80808080, 0xFF00FF00, 0x02020202, 0x00FF00FF, 0x00000080]
+    ab, bb = a.view(np.uint8).reshape(-1, 4), b.view(np.uint8).reshape(-1, 4)
+    sub = (ab.astype(np.int32) - bb).astype(np.uint8).view(np.uint32).reshape(-1)
+    add = (ab.astype(np.int32) + bb).astype(np.uint8).view(np.uint32).reshape(-1)
+    xc = (ab ^ (ab >> 1)).view(np.uint32).reshape(-1)
+    xf = (ab ^ np.where(ab & 0x80, 0x7F, 0).astype(np.uint8)).view(np.uint32).reshape(-1)
+    for i in range(a.size):
+        assert swar.t_sub(int(a[i]), int(b[i])) == int(sub[i])
+        assert swar.t_add(int(a[i]), int(b[i])) == int(add[i])
+        assert swar.t_xc(int(a[i]), 0) == int(xc[i]) and swar.t_xf(int(a[i]), 0) == int(xf[i])
+        keep = swar.t_xc(int(a[i]), 0xFF)  # byte lane 0 untouched (column 0, XORModule.cpp:12)
+        assert keep & 0xFF == int(a[i]) & 0xFF and keep >> 8 == int(xc[i]) >> 8
+        keep = swar.t_xf(int(a[i]), 0xFF)
+        assert keep & 0xFF == int(a[i]) & 0xFF and keep >> 8 == int(xf[i]) >> 8
+
+
+def test_zero_runs_and_leading_zero_rows(swar):
+    rng = np.random.default_rng(4)
+    masks = [0, 2**64 - 1, 1, 2**63, 0b1011, 0x5555555555555555, 0xAAAAAAAAAAAAAAAA] + \
+        [int(v) for v in rng.integers(0, 2**63, 3000)] + [int(v) & int(w) for v, w in zip(rng.integers(0, 2**63, 2000), rng.integers(0, 2**63, 2000))]
+    for z in masks:
+        cost, run = 0, 0
+        for i in range(64):  # FPCModule.cpp:27-45, 69-79
+            if (z >> i) & 1:
+                run += 1
+            elif run:
+                cost += 7 if run > 1 else 4
+                run = 0
+        if run:
+            cost += 7 if run > 1 else 4
+        assert swar.t_zero_run_cost(z) == cost, hex(z)
+        lz = 0
+        while lz < 64 and (z >> lz) & 1:
+            lz += 1
+        assert swar.t_lzr(z, 64) == lz
+        assert swar.t_lzr(z & 0xFFFF, 16) == min(lz, 16)
