@@ -44,11 +44,32 @@ MPC_HD uint32_t add_u16x2(uint32_t a, uint32_t b) {
 #endif
 }
 
+// x >> n issued on the FMA pipe (IMAD.HI) instead of the ALU pipe (SHF): the kernels are ALU-pipe bound
+MPC_HD uint32_t shr_fma(uint32_t x, int n) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(1u << (32 - n)));
+  return d;
+#else
+  return x >> n;
+#endif
+}
+// a - b issued on the FMA pipe (IMAD) instead of the ALU pipe (IADD3)
+MPC_HD uint32_t sub_fma(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(d) : "r"(b), "r"(a));
+  return d;
+#else
+  return a - b;
+#endif
+}
+
 // ---- per-byte modular arithmetic on 4 packed bytes -----------------------------------------------
 // (a - b) mod 256 per byte.  ResidueModule::ProcessLine, ResidueModule.cpp:34.
 MPC_HD uint32_t sub_u8x4(uint32_t a, uint32_t b) {
   const uint32_t H = 0x80808080u;
-  uint32_t t = (a | H) - (b & ~H);
+  uint32_t t = sub_fma(a | H, b & ~H);
   return t ^ ((a ^ ~b) & H);
 }
 // (a + b) mod 256 per byte.  DiffBasePredictor::PredictLine, PredictorModule.cpp:104.
@@ -81,9 +102,9 @@ MPC_HD uint32_t row2_cost(uint32_t w, uint32_t* nz_out) {
   uint32_t t = add_u16x2(w, 0xffffffffu);  // row - 1 per halfword (no borrow across the halves)
   uint32_t s = w & t;                 // row with its lowest set bit cleared: != 0 <=> two or more ones
   uint32_t lb = w & ~t;               // lowest set bit (0 for a zero row)
-  uint32_t x = ((s >> 1) & 0x7fff7fffu) ^ lb;  // == 0 <=> exactly two ones, adjacent (or fewer than two ones)
+  uint32_t x = (shr_fma(s, 1) & 0x7fff7fffu) ^ lb;  // == 0 <=> exactly two ones, adjacent (or fewer than two ones)
   uint32_t back = w & 0x00ff00ffu;
-  uint32_t front = (w >> 8) & 0x00ff00ffu;
+  uint32_t front = shr_fma(w, 8) & 0x00ff00ffu;
   uint32_t a = min3_u16x2(s, x, ONE);          // 1 <=> >= 2 ones and not "two consecutive"
   uint32_t b3 = min3_u16x2(a, front, back);    // 1 <=> additionally both halves non-zero
   uint32_t ns = min_u16x2(s, ONE);
