@@ -39,6 +39,14 @@ class StatsPod(C.Structure):
                 ("hist", (C.c_uint64 * HIST_BINS) * (MAX_MODULES + 1))]
 
 
+class VariantStats(C.Structure):
+    _fields_ = [("blocks", C.c_uint64), ("original_bits", C.c_uint64), ("compressed_bits", C.c_uint64),
+                ("counts", C.c_uint64 * 16)]
+
+
+ALG = {"BDI": 1, "FPC": 2, "BPC": 3}
+
+
 class MpcError(RuntimeError):
     pass
 
@@ -50,7 +58,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpc_b200
 SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config_validate", "mpc_create",
            "mpc_destroy", "mpc_last_error", "mpc_global_error", "mpc_set_kernel", "mpc_kernel_name", "mpc_set_stream",
            "mpc_submit_device", "mpc_submit_host", "mpc_sync", "mpc_stats_device_ptr", "mpc_finish",
-           "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version"]
+           "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version",
+           "mpc_variant_run_device", "mpc_variant_run_host", "mpc_variant_error"]
 
 
 def lib():
@@ -84,6 +93,9 @@ def lib():
     l.mpc_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     l.mpc_synth_device.argtypes = [vp, vp, u64, u64, u64, C.c_int, u64]
     l.mpc_version.restype = C.c_char_p
+    l.mpc_variant_run_device.argtypes = [C.c_int, C.c_int, vp, u64, C.c_uint32, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
+    l.mpc_variant_run_host.argtypes = [C.c_int, C.c_int, vp, u64, C.c_uint32, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
+    l.mpc_variant_error.restype = C.c_char_p
     _LIB = l
     return l
 
@@ -214,6 +226,24 @@ class Mpc:
         self.submit_host(lines, packed)
         st = self.finish()
         return (packed & 0x7FF).astype(np.uint32), (packed >> 11).astype(np.int32) - 1, st
+
+
+def variant_run(alg, lines=None, device_ptr=None, n_blocks=None, device=0, want_sizes=True, line_size=128):
+    """BDI / FPC / BPC over host blocks (numpy) or a device pointer -> (sizes or None, VariantStats, kernel_ms)."""
+    st, ms = VariantStats(), C.c_float()
+    aid = ALG[alg] if isinstance(alg, str) else alg
+    if device_ptr is None:
+        lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, line_size)
+        n = lines.shape[0]
+        sizes = np.zeros(n, dtype=np.uint16) if want_sizes else None
+        rc = lib().mpc_variant_run_host(aid, device, lines.ctypes.data, n, line_size,
+                                        sizes.ctypes.data if want_sizes else None, C.byref(st), C.byref(ms))
+    else:
+        sizes = None
+        rc = lib().mpc_variant_run_device(aid, device, device_ptr, n_blocks, line_size, None, C.byref(st), C.byref(ms))
+    if rc != 0:
+        raise MpcError(f"variant {alg} failed ({rc}): {lib().mpc_variant_error().decode()}")
+    return sizes, st, ms.value
 
 
 def unpack(packed):

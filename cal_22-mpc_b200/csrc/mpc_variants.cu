@@ -1,0 +1,165 @@
+// GPU size models of the stateless secondary compressors BDI / FPC / BPC (BASELINE.json config #5): one block per
+// thread, same tile loader as the specialised MPC kernel.  Replaces comp::BDI/FPC/BPC::CompressLine
+// (reference src/compressor/BDI.cpp:6, FPC.cpp:7, BPC.cpp:20) driven from main.cpp:237-243.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "mpc_capi.h"
+#include "mpc_tile.cuh"
+#include "mpc_variants.cuh"
+
+namespace mpc {
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kCounters = 16;  // device layout: [0] compressed bits, [1..16] counters
+
+template <int ALG>
+__global__ void __launch_bounds__(kThreads)
+variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __restrict__ sizes,
+               unsigned long long* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* s_stage = reinterpret_cast<uint4*>(smem_raw);
+  __shared__ unsigned long long s_cnt[1 + kCounters];
+  if (threadIdx.x < 1 + kCounters) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long bits = 0;
+  tile::for_each_block(lines, n_blocks, s_stage + warp * tile::kStages * 256, kWarps,
+                       [&](const uint32_t (&x)[32], uint64_t blk, bool valid) {
+    uint32_t size = 0;
+    uint64_t packed = 0;  // eight 8-bit counters
+    uint32_t extra = 0;
+    if (ALG == MPC_ALG_BDI) {
+      int st;
+      size = mpcvar::bdi_block(x, &st);
+      packed = 1ull << (4 * st);  // nine 4-bit one-hot counters
+    } else if (ALG == MPC_ALG_FPC) {
+      size = mpcvar::fpc_block(x, &packed);
+    } else {
+      size = mpcvar::bpc_block(x, &packed, &extra);
+    }
+    if (!valid) { size = 0; packed = 0; extra = 0; }
+    if (valid && sizes) sizes[blk] = (uint16_t)size;
+    bits += size;
+    // warp-aggregate the small counters, one shared atomic per counter per tile
+    if (ALG == MPC_ALG_BDI) {
+#pragma unroll
+      for (int s = 0; s < 9; s++) {
+        const uint32_t c = __popc(__ballot_sync(0xffffffffu, (packed >> (4 * s)) & 1ull));
+        if (lane == 0 && c) atomicAdd(&s_cnt[1 + s], (unsigned long long)c);
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)((packed >> (8 * p)) & 0xffull));
+        if (lane == 0 && c) atomicAdd(&s_cnt[1 + p], (unsigned long long)c);
+      }
+      if (ALG == MPC_ALG_BPC) {
+        const uint32_t c = __reduce_add_sync(0xffffffffu, extra);
+        if (lane == 0 && c) atomicAdd(&s_cnt[1 + 8], (unsigned long long)c);
+      }
+    }
+  });
+  // per-thread bit totals -> warp -> CTA -> global
+  for (int o = 16; o; o >>= 1) bits += __shfl_down_sync(0xffffffffu, bits, o);
+  if (lane == 0 && bits) atomicAdd(&s_cnt[0], bits);
+  __syncthreads();
+  if (threadIdx.x < 1 + kCounters && s_cnt[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+thread_local std::string g_verr;
+
+int vfail(int code, const char* what, cudaError_t e) {
+  g_verr = std::string(what) + ": " + cudaGetErrorString(e);
+  return code;
+}
+
+template <int ALG>
+cudaError_t launch_variant(const uint8_t* d_lines, uint64_t n, uint16_t* d_sizes, unsigned long long* d_stats, int sms,
+                           cudaStream_t s) {
+  const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
+  cudaError_t e = cudaFuncSetAttribute(variant_kernel<ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, variant_kernel<ALG>, kThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const uint64_t tiles = (n + tile::kTileBlocks - 1) / tile::kTileBlocks;
+  uint64_t grid = (uint64_t)sms * per_sm;
+  const uint64_t want = (tiles + kWarps - 1) / kWarps;
+  if (grid > want) grid = want;
+  variant_kernel<ALG><<<(unsigned)grid, kThreads, smem, s>>>(reinterpret_cast<const uint4*>(d_lines), n, d_sizes, d_stats);
+  return cudaGetLastError();
+}
+
+}  // namespace
+}  // namespace mpc
+
+extern "C" const char* mpc_variant_error(void) { return mpc::g_verr.c_str(); }
+
+extern "C" int mpc_variant_run_device(int alg, int device, const uint8_t* d_lines, uint64_t n_blocks, uint32_t line_size,
+                                      uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms) {
+  using namespace mpc;
+  if (!out || (n_blocks && !d_lines)) { g_verr = "null argument"; return MPC_E_ARG; }
+  if (alg < MPC_ALG_BDI || alg > MPC_ALG_BPC) { g_verr = "unknown algorithm id"; return MPC_E_ARG; }
+  if (line_size != 128) { g_verr = "the GPU variants are built for 128-byte blocks"; return MPC_E_ARG; }
+  if ((uintptr_t)d_lines & 15) { g_verr = "lines must be 16-byte aligned"; return MPC_E_ARG; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return vfail(MPC_E_CUDA, "cudaSetDevice", e);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  unsigned long long* d_stats = nullptr;
+  if ((e = cudaMalloc(&d_stats, (1 + kCounters) * sizeof(unsigned long long))) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMalloc", e);
+  cudaMemset(d_stats, 0, (1 + kCounters) * sizeof(unsigned long long));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  if (n_blocks) {
+    if (alg == MPC_ALG_BDI) e = launch_variant<MPC_ALG_BDI>(d_lines, n_blocks, d_sizes, d_stats, sms, 0);
+    else if (alg == MPC_ALG_FPC) e = launch_variant<MPC_ALG_FPC>(d_lines, n_blocks, d_sizes, d_stats, sms, 0);
+    else e = launch_variant<MPC_ALG_BPC>(d_lines, n_blocks, d_sizes, d_stats, sms, 0);
+  }
+  cudaEventRecord(e1, 0);
+  unsigned long long h[1 + kCounters];
+  if (e == cudaSuccess) e = cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_stats);
+  if (e != cudaSuccess) return vfail(MPC_E_CUDA, "variant kernel", e);
+  memset(out, 0, sizeof(*out));
+  out->blocks = n_blocks;
+  out->original_bits = n_blocks * 8ull * line_size;  // CompResult::OriginalSize
+  out->compressed_bits = h[0];                       // CompResult::CompressedSize
+  for (int i = 0; i < kCounters; i++) out->counts[i] = h[1 + i];
+  if (kernel_ms) *kernel_ms = ms;
+  return MPC_OK;
+}
+
+extern "C" int mpc_variant_run_host(int alg, int device, const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size,
+                                    uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms) {
+  using namespace mpc;
+  if (n_blocks && !h_lines) { g_verr = "null lines"; return MPC_E_ARG; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return vfail(MPC_E_CUDA, "cudaSetDevice", e);
+  uint8_t* d_lines = nullptr;
+  uint16_t* d_sizes = nullptr;
+  const size_t bytes = (size_t)n_blocks * line_size;
+  if ((e = cudaMalloc(&d_lines, bytes ? bytes : 16)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMalloc", e);
+  if (h_sizes && (e = cudaMalloc(&d_sizes, (n_blocks ? n_blocks : 1) * sizeof(uint16_t))) != cudaSuccess) {
+    cudaFree(d_lines);
+    return vfail(MPC_E_CUDA, "cudaMalloc", e);
+  }
+  if (bytes) cudaMemcpy(d_lines, h_lines, bytes, cudaMemcpyHostToDevice);
+  int rc = mpc_variant_run_device(alg, device, d_lines, n_blocks, line_size, d_sizes, out, kernel_ms);
+  if (rc == MPC_OK && h_sizes && n_blocks) cudaMemcpy(h_sizes, d_sizes, n_blocks * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_lines);
+  if (d_sizes) cudaFree(d_sizes);
+  return rc;
+}

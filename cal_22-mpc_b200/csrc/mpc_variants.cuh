@@ -1,0 +1,181 @@
+// Per-block size models of the stateless secondary compressors (BDI, FPC, BPC) for 128-byte blocks held as 32
+// little-endian words.  __host__ __device__ so that the same code is checked on the CPU (tests/test_swar_host.py)
+// and runs one block per thread on the GPU (mpc_variants.cu).  Reference: src/compressor/{BDI,FPC,BPC}.cpp;
+// observable quirks are kept.
+#pragma once
+#include <stdint.h>
+
+#include "mpc_device.cuh"
+
+namespace mpcvar {
+
+MPC_HD int clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return v ? __builtin_clzll(v) : 64;
+#endif
+}
+MPC_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+MPC_HD int popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(v);
+#else
+  return __builtin_popcountll(v);
+#endif
+}
+
+// ---- BDI ------------------------------------------------------------------------------------------------------
+// BDI::reduceSign, BDI.cpp:203-218: a negative value keeps (index of its highest zero bit + 2) low bits; all ones
+// comes back unchanged (and therefore never fits a delta).
+MPC_HD uint64_t bdi_reduce_sign(uint64_t x) {
+  if ((x >> 63) == 0 || x == ~0ull) return x;
+  const int hz = 63 - clz64(~x);  // highest zero bit, 0..62
+  const int keep = hz + 2;        // 2..64
+  return keep >= 64 ? x : (x & ((1ull << keep) - 1ull));
+}
+
+template <int B>
+MPC_HD uint64_t bdi_value(const uint32_t (&x)[32], int i) {  // little-endian chunk, zero-extended (BDI.cpp:127-153)
+  if (B == 8) return (uint64_t)x[2 * i] | ((uint64_t)x[2 * i + 1] << 32);
+  if (B == 4) return x[i];
+  return (x[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+}
+
+// BDI::checkBDI, BDI.cpp:108-201
+template <int B, int D>
+MPC_HD uint32_t bdi_check(const uint32_t (&x)[32]) {
+  constexpr int n = 128 / B;
+  constexpr uint64_t limit = D == 1 ? 0xffull : D == 2 ? 0xffffull : 0xffffffffull;
+  uint64_t imm_mask = 0;
+#pragma unroll
+  for (int i = 0; i < n; i++)
+    if (bdi_reduce_sign(bdi_value<B>(x, i)) <= limit) imm_mask |= 1ull << i;
+  const uint32_t imm = (uint32_t)popc64(imm_mask);
+  bool have_base = false, not_all = false;
+  uint64_t base = 0;
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    if ((imm_mask >> i) & 1ull) continue;
+    const uint64_t v = bdi_value<B>(x, i);
+    if (!have_base) { base = v; have_base = true; }
+    else if (bdi_reduce_sign(base - v) > limit) not_all = true;
+  }
+  if (not_all) return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)n - imm) * (uint32_t)B);
+  return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)B + ((uint32_t)n - imm - 1u) * (uint32_t)D));  // wraps when imm == n
+}
+
+// BDI::CompressLine, BDI.cpp:6-74.  Returns bits incl. the 4 encoding bits; *state = BDIState (BDI.h:10-21).
+MPC_HD uint32_t bdi_block(const uint32_t (&x)[32], int* state) {
+  uint32_t any = 0, rep = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) { any |= x[i]; rep |= x[i] ^ x[i & 1]; }
+  uint32_t best = 1024u;
+  int sel = 8;
+  if (any == 0) { best = 8; sel = 0; }
+  else if (rep == 0) { best = 64; sel = 1; }
+  else {
+    uint32_t cur;
+    cur = bdi_check<8, 1>(x); if (best > cur) { best = cur; sel = 2; }
+    cur = bdi_check<8, 2>(x); if (best > cur) { best = cur; sel = 3; }
+    cur = bdi_check<8, 4>(x); if (best > cur) { best = cur; sel = 4; }
+    cur = bdi_check<4, 1>(x); if (best > cur) { best = cur; sel = 5; }
+    cur = bdi_check<4, 2>(x); if (best > cur) { best = cur; sel = 6; }
+    cur = bdi_check<2, 1>(x); if (best > cur) { best = cur; sel = 7; }
+    if (best == 1024u) sel = 8;
+  }
+  *state = sel;
+  return best + 4u;
+}
+
+// ---- FPC ------------------------------------------------------------------------------------------------------
+// FPC::CompressLine, FPC.cpp:7-87.  counts8 packs the eight per-word prefix counters, 8 bits each (<= 32 per block).
+// The reference's unbounded zero-run scan (FPC.cpp:26) is bounded at the block end here.
+MPC_HD uint32_t fpc_block(const uint32_t (&x)[32], uint64_t* counts8) {
+  uint32_t size = 0;
+  uint64_t cnt = 0;
+  bool prev_zero = false;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const uint32_t v = x[i];
+    int p;
+    uint32_t c;
+    if (v == 0) { p = 0; c = prev_zero ? 0u : 6u; }
+    else if ((v & 0xFFFFFFF8u) == 0 || (v & 0xFFFFFFF8u) == 0xFFFFFFF8u) { p = 1; c = 7; }
+    else if ((v & 0xFFFFFF80u) == 0 || (v & 0xFFFFFF80u) == 0xFFFFFF80u) { p = 2; c = 11; }
+    else if ((v & 0xFFFF8000u) == 0 || (v & 0xFFFF8000u) == 0xFFFF8000u) { p = 3; c = 19; }
+    else if ((v & 0x0000FFFFu) == 0) { p = 4; c = 19; }
+    else if ((v & 0xFF80FF80u) == 0 || (v & 0xFF80FF80u) == 0xFF800000u || (v & 0xFF80FF80u) == 0x0000FF80u ||
+             (v & 0xFF80FF80u) == 0xFF80FF80u) { p = 5; c = 19; }
+    else if (v == (v & 0xffu) * 0x01010101u) { p = 6; c = 11; }
+    else { p = 7; c = 35; }
+    prev_zero = (v == 0);
+    size += c;
+    cnt += 1ull << (8 * p);
+  }
+  *counts8 = cnt;
+  return size;
+}
+
+// ---- BPC ------------------------------------------------------------------------------------------------------
+// 32x32 bit-matrix transpose in registers: afterwards bit r of a[c] is the former bit c of a[r].
+MPC_HD void transpose32(uint32_t (&a)[32]) {
+  uint32_t m = 0x0000ffffu;
+#pragma unroll
+  for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+    for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+      const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+      a[k] ^= t << j;
+      a[k + j] ^= t;
+    }
+  }
+}
+
+// BPC::CompressLine, BPC.cpp:20-87 + encodeFirst (always 7, BPC.cpp:89-101) + encodeDeltas (BPC.cpp:103-185).
+// pat8 packs the 7 pattern counters (BPC.h:13-22), 8 bits each; *words = value added to TotalWords.
+MPC_HD uint32_t bpc_block(const uint32_t (&x)[32], uint64_t* pat8, uint32_t* words) {
+  uint32_t d[32];
+  uint32_t neg = 0;  // bit r = delta r negative = bit 32 of the 33-bit delta (words are zero-extended, BPC.cpp:41-45)
+#pragma unroll
+  for (int r = 0; r < 31; r++) {
+    d[r] = x[r + 1] - x[r];
+    neg |= (x[r + 1] < x[r] ? 1u : 0u) << r;
+  }
+  d[31] = 0;
+  transpose32(d);  // d[c] = delta bit plane c (bit r = delta r)
+  uint32_t length = 7, run = 0, nwords = 0;
+  uint64_t pat = 0;
+  uint32_t prev = neg;  // DBP[32]
+#pragma unroll
+  for (int i = 32; i >= 0; i--) {
+    const uint32_t dbp = (i == 32) ? neg : d[i];
+    const uint32_t dbx = (i == 32) ? neg : (dbp ^ prev);
+    prev = dbp;
+    if (dbx == 0) { run++; continue; }
+    if (run) { length += (run == 1) ? 3u : 7u; pat += 1ull << 8; nwords += run; run = 0; }
+    int p;
+    if (dbp == 0) { length += 5; p = 2; }
+    else if (dbx == 0x7fffffffu) { length += 5; p = 6; }
+    else {
+      const int ones = popc32(dbx);
+      if (ones == 1) { length += 10; p = 3; }
+      else if (ones == 2 && (dbx & (dbx >> 1))) { length += 10; p = 4; }
+      else { length += 32; p = 0; }
+    }
+    pat += 1ull << (8 * p);
+    nwords += 1;
+  }
+  if (run) { length += (run == 1) ? 3u : 7u; pat += 1ull << 8; nwords += run; }
+  *pat8 = pat;
+  *words = nwords;
+  return length;
+}
+
+}  // namespace mpcvar

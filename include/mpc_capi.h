@@ -152,6 +152,25 @@ enum {
 int mpc_synth_device(mpc_ctx* ctx, uint8_t* d_lines, uint64_t first_block, uint64_t n_blocks,
                      uint64_t total_blocks, int kind, uint64_t seed);
 
+/* ---- stateless secondary compressors (BASELINE.json config #5) -------------------------------------------- */
+
+enum { MPC_ALG_BDI = 1, MPC_ALG_FPC = 2, MPC_ALG_BPC = 3 };
+/* counts: BDI = the nine BDIState counters (BDI.h:29-33); FPC = the eight per-word prefix counters (FPC.h:31-37;
+ * TotalWords = their sum); BPC = the seven BPCPattern counters, counts[7] = TotalWords (BPC.h:29-33). */
+typedef struct {
+  uint64_t blocks, original_bits, compressed_bits;
+  uint64_t counts[16];
+} mpc_variant_stats;
+/* One pass of comp::BDI / comp::FPC / comp::BPC::CompressLine (BDI.cpp:6, FPC.cpp:7, BPC.cpp:20) over n_blocks
+ * 128-byte blocks.  sizes (optional): compressed bits per block.  FPC: the reference's zero-run scan reads past
+ * the end of the line (FPC.cpp:26); here it stops at the block end -- sizes are identical, per-word statistics
+ * are the deterministic ones. */
+int mpc_variant_run_device(int alg, int device, const uint8_t* d_lines, uint64_t n_blocks, uint32_t line_size,
+                           uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms);
+int mpc_variant_run_host(int alg, int device, const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size,
+                         uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms);
+const char* mpc_variant_error(void);
+
 /* ---- library info ---------------------------------------------------------------------- */
 const char* mpc_version(void);
 

@@ -37,8 +37,22 @@ def oracle_lib():
         l.orc_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_uint, C.c_int]
         l.orc_run.restype = None
+        l.orc_variant_run.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint, C.c_void_p, C.c_void_p]
+        l.orc_variant_run.restype = None
         _oracle = l
     return _oracle
+
+
+VARIANT_ID = {"BDI": 1, "FPC": 2, "BPC": 3}
+
+
+def oracle_variant(alg, lines, L=128):
+    """CPU oracle of BDI / FPC / BPC: -> (sizes uint32 [n], counts uint64 [16])"""
+    lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, L)
+    sizes = np.zeros(lines.shape[0], dtype=np.uint32)
+    counts = np.zeros(16, dtype=np.uint64)
+    oracle_lib().orc_variant_run(VARIANT_ID[alg], lines.ctypes.data, lines.shape[0], L, sizes.ctypes.data, counts.ctypes.data)
+    return sizes, counts
 
 
 def have_ref():

@@ -19,3 +19,27 @@ void t_row_costs(unsigned other, unsigned* lo, unsigned* hi) {
   }
 }
 }
+
+// ---- secondary variants (csrc/mpc_variants.cuh) on the host ----
+#include "mpc_variants.cuh"
+extern "C" void t_variant_run(int alg, const unsigned char* lines, unsigned long long n, unsigned* sizes, unsigned long long* counts) {
+  for (unsigned long long i = 0; i < n; i++) {
+    uint32_t x[32];
+    __builtin_memcpy(x, lines + i * 128, 128);
+    if (alg == 1) {
+      int st;
+      sizes[i] = mpcvar::bdi_block(x, &st);
+      counts[st]++;
+    } else if (alg == 2) {
+      uint64_t c8;
+      sizes[i] = mpcvar::fpc_block(x, &c8);
+      for (int p = 0; p < 8; p++) counts[p] += (c8 >> (8 * p)) & 0xff;
+    } else {
+      uint64_t p8;
+      uint32_t w;
+      sizes[i] = mpcvar::bpc_block(x, &p8, &w);
+      for (int p = 0; p < 7; p++) counts[p] += (p8 >> (8 * p)) & 0xff;
+      counts[7] += w;
+    }
+  }
+}

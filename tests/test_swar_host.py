@@ -89,3 +89,21 @@ def test_zero_runs_and_leading_zero_rows(swar):
             lz += 1
         assert swar.t_lzr(z, 64) == lz
         assert swar.t_lzr(z & 0xFFFF, 16) == min(lz, 16)
+
+
+@pytest.mark.parametrize("alg", ["BDI", "FPC", "BPC"])
+def test_variant_block_functions_match_oracle(swar, alg):
+    """csrc/mpc_variants.cuh (the code the GPU runs per thread) compiled for the host vs the C oracle."""
+    from helpers import random_blocks
+    from oracle.bridge import VARIANT_ID, oracle_variant
+    from tools.gen_dump import kat_blocks, synth
+    rng = np.random.default_rng(8)
+    d = np.concatenate([kat_blocks(), synth("mixed_hashed", 3, 0, 4000, 4000), random_blocks(rng, 3000)])
+    want_sizes, want_counts = oracle_variant(alg, d)
+    sizes = np.zeros(d.shape[0], np.uint32)
+    counts = np.zeros(16, np.uint64)
+    swar.t_variant_run.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+    swar.t_variant_run(VARIANT_ID[alg], d.ctypes.data, d.shape[0], sizes.ctypes.data, counts.ctypes.data)
+    bad = np.nonzero(sizes != want_sizes)[0]
+    assert bad.size == 0, (bad[:5], sizes[bad[:5]], want_sizes[bad[:5]])
+    assert np.array_equal(counts, want_counts)

@@ -454,8 +454,12 @@ def generate(cfg_path):
     out.append("  // VPC.cpp:372-395: most leading zero rows wins, ties go to the later module")
     out.append("  __device__ static __forceinline__ void select(const uint32_t (&x)[32], int& best, uint32_t& bestz) {")
     out.append("    uint32_t z;")
-    for m in mods:
+    for m in mods[:-1]:
         out.append(f"    z = score_{m.idx}(x); if (bestz <= z) {{ best = {m.idx}; bestz = z; }}")
+    if mods:
+        m = mods[-1]
+        out.append("    // the last module wins every tie, so while no earlier module has a zero row it wins unscored")
+        out.append(f"    if (bestz == 0u) {{ best = {m.idx}; }} else {{ z = score_{m.idx}(x); if (bestz <= z) {{ best = {m.idx}; bestz = z; }} }}")
     out.append("  }")
     out.append("  // residue sums (VPC.cpp:417-443) + common encoder (FPCModule.cpp:19-85) of the chosen module")
     out.append("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq) {")
