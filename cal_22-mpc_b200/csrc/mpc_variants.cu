@@ -60,7 +60,7 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
       }
       if (ALG == MPC_ALG_BPC) {
         const uint32_t c = __reduce_add_sync(0xffffffffu, extra);
-        if (lane == 0 && c) atomicAdd(&s_cnt[1 + 8], (unsigned long long)c);
+        if (lane == 0 && c) atomicAdd(&s_cnt[1 + 7], (unsigned long long)c);  // counts[7] = TotalWords
       }
     }
   });

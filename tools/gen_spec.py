@@ -444,6 +444,9 @@ def generate(cfg_path):
     out.append(f"  static constexpr int kNumModules = {n};")
     out.append(f"  static constexpr int kFirst = {first};")
     out.append(f"  static constexpr bool kHasWordSame = {'true' if has_ws else 'false'};")
+    # register budget: plane-major modules keep the line, its residues and the transposed rows live at once
+    min_ctas = int(os.environ.get("MPC_SPEC_MIN_CTAS", "0")) or (1 if any(m.family == "pm" for m in mods) else 2)
+    out.append(f"  static constexpr int kMinCtasPerSm = {min_ctas};  // __launch_bounds__: 2 -> <= 128 registers, 1 -> <= 255")
     out.append("  __device__ static __forceinline__ uint32_t enc(int k) {  // encoding bits of cluster k-1, VPC.cpp:102-117")
     out.append("    switch (k) {")
     for k, e in enumerate(enc):
@@ -452,7 +455,7 @@ def generate(cfg_path):
     out.append("    return 0u;")
     out.append("  }")
     out.append("  // VPC.cpp:372-395: most leading zero rows wins, ties go to the later module")
-    out.append("  __device__ static __forceinline__ void select(const uint32_t (&x)[32], int& best, uint32_t& bestz) {")
+    out.append("  __device__ static __forceinline__ void select(const uint32_t (&x)[32], int& best, uint32_t& bestz, unsigned lanes) {")
     out.append("    uint32_t z;")
     for m in mods[:-1]:
         out.append(f"    z = score_{m.idx}(x); if (bestz <= z) {{ best = {m.idx}; bestz = z; }}")
@@ -460,9 +463,10 @@ def generate(cfg_path):
         m = mods[-1]
         out.append("    // the last module wins every tie, so while no earlier module has a zero row it wins unscored")
         out.append(f"    if (bestz == 0u) {{ best = {m.idx}; }} else {{ z = score_{m.idx}(x); if (bestz <= z) {{ best = {m.idx}; bestz = z; }} }}")
+        out.append("    __syncwarp(lanes);  // reconverge before the encoder: both sides of the branch share it")
     out.append("  }")
     out.append("  // residue sums (VPC.cpp:417-443) + common encoder (FPCModule.cpp:19-85) of the chosen module")
-    out.append("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq) {")
+    out.append("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq, unsigned lanes) {")
     out.append("    uint32_t c[32];")
     fams = sorted(set((m.family, pm_selectors(m.rho) if m.family == "pm" else None) for m in mods), key=str)
     out.append("    int fam = 0;")
@@ -472,6 +476,7 @@ def generate(cfg_path):
         out.append(f"      case {m.idx}: full_{m.idx}(x, c, sa, sq); fam = {fid}; break;")
     out.append("      default: break;")
     out.append("    }")
+    out.append("    __syncwarp(lanes);  // the row classifier below is shared by all modules: run it once per warp")
     if len(fams) == 1:
         fam, sels = fams[0]
         out.append("    (void)fam;")
