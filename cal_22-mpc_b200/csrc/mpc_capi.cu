@@ -39,6 +39,7 @@ struct mpc_ctx {
   mpc::GenericParams gparams;
   mpc::GenericModule* d_gmods = nullptr;
   const mpc::SpecKernel* spec = nullptr;  // specialised kernel matching cfg, if any
+  uint8_t* d_row_lut = nullptr;           // row-cost table used by the specialised kernels
   int kernel_choice = 0;
   uint64_t* d_stats = nullptr;
   cudaStream_t own_stream = nullptr;      // created by mpc_create
@@ -85,7 +86,7 @@ void refresh_kernel_name(mpc_ctx* ctx) {
 int launch(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n, uint16_t* d_packed, cudaStream_t s) {
   cudaError_t e;
   if (use_spec(ctx))
-    e = ctx->spec->launch(ctx->cfg, d_lines, n, d_packed, ctx->d_stats, ctx->sm_count, s);
+    e = ctx->spec->launch(ctx->cfg, d_lines, n, d_packed, ctx->d_stats, ctx->d_row_lut, ctx->sm_count, s);
   else
     e = mpc::launch_generic(ctx->gparams, ctx->d_gmods, d_lines, n, d_packed, ctx->d_stats, ctx->sm_count, s);
   if (e != cudaSuccess) return fail(ctx, MPC_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -166,6 +167,12 @@ int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out) {
   const size_t gbytes = sizeof(mpc::GenericModule) * (size_t)(ctx->gparams.num_predcomp > 0 ? ctx->gparams.num_predcomp : 1);
   MPC_CREATE_CUDA(cudaMalloc(&ctx->d_gmods, gbytes));
   MPC_CREATE_CUDA(cudaMemcpyAsync(ctx->d_gmods, gm.data(), gbytes, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    std::vector<uint8_t> lut(65536);
+    mpc::build_row_cost_lut(lut.data());
+    MPC_CREATE_CUDA(cudaMalloc(&ctx->d_row_lut, lut.size()));
+    MPC_CREATE_CUDA(cudaMemcpy(ctx->d_row_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
+  }
   MPC_CREATE_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef MPC_CREATE_CUDA
   ctx->spec = mpc::find_spec_kernel(ctx->cfg);
@@ -189,6 +196,7 @@ void mpc_destroy(mpc_ctx* ctx) {
     if (st.done) cudaEventDestroy(st.done);
   }
   if (ctx->d_gmods) cudaFree(ctx->d_gmods);
+  if (ctx->d_row_lut) cudaFree(ctx->d_row_lut);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);

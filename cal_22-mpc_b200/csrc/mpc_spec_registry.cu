@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "mpc_spec.h"
+#include "mpc_device.cuh"
 
 namespace mpc {
 
@@ -33,6 +34,13 @@ bool spec_pod_equal(const mpc_config_pod& a, const mpc_config_pod& b) {
     }
   }
   return true;
+}
+
+void build_row_cost_lut(uint8_t* lut) {
+  for (uint32_t v = 0; v < 65536; v++) {
+    uint32_t nz;
+    lut[v] = (uint8_t)(mpcdev::row2_cost(v, &nz) & 0xffu);
+  }
 }
 
 const SpecKernel* find_spec_kernel(const mpc_config_pod& cfg) {

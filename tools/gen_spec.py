@@ -446,7 +446,17 @@ def generate(cfg_path):
     out.append(f"  static constexpr bool kHasWordSame = {'true' if has_ws else 'false'};")
     # register budget: plane-major modules keep the line, its residues and the transposed rows live at once
     min_ctas = int(os.environ.get("MPC_SPEC_MIN_CTAS", "0")) or (1 if any(m.family == "pm" for m in mods) else 2)
-    out.append(f"  static constexpr int kMinCtasPerSm = {min_ctas};  // __launch_bounds__: 2 -> <= 128 registers, 1 -> <= 255")
+    has_pm = any(m.family == "pm" for m in mods)
+    has_cm = any(m.family == "cm" for m in mods)
+    use_lut = has_cm and os.environ.get("MPC_SPEC_LUT", "1") != "0"
+    # column-major only: 16 warps in ONE CTA per SM (<= 128 registers) so that the 64 KiB row-cost table, the
+    # 128 KiB of tile stages and the histogram fit the 227 KiB of shared memory
+    warps = 16 if (use_lut and not has_pm) else 8
+    if warps == 16:
+        min_ctas = 1
+    out.append(f"  static constexpr int kWarps = {warps};")
+    out.append(f"  static constexpr bool kUseLut = {'true' if use_lut else 'false'};  // shared-memory row-cost table (column-major modules)")
+    out.append(f"  static constexpr int kMinCtasPerSm = {min_ctas};  // __launch_bounds__: register budget 65536 / (threads * CTAs)")
     out.append("  __device__ static __forceinline__ uint32_t enc(int k) {  // encoding bits of cluster k-1, VPC.cpp:102-117")
     out.append("    switch (k) {")
     for k, e in enumerate(enc):
@@ -466,7 +476,7 @@ def generate(cfg_path):
         out.append("    __syncwarp(lanes);  // reconverge before the encoder: both sides of the branch share it")
     out.append("  }")
     out.append("  // residue sums (VPC.cpp:417-443) + common encoder (FPCModule.cpp:19-85) of the chosen module")
-    out.append("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq, unsigned lanes) {")
+    out.append("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq, unsigned lanes, const uint8_t* lut) {")
     out.append("    uint32_t c[32];")
     fams = sorted(set((m.family, pm_selectors(m.rho) if m.family == "pm" else None) for m in mods), key=str)
     out.append("    int fam = 0;")
@@ -480,10 +490,10 @@ def generate(cfg_path):
     if len(fams) == 1:
         fam, sels = fams[0]
         out.append("    (void)fam;")
-        out.append("    return " + ("encode_cm(c);" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c);"))
+        out.append("    return " + ("encode_cm<kUseLut>(c, lut);" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c);"))
     else:
         for fid, (fam, sels) in enumerate(fams):
-            call = "encode_cm(c)" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c)"
+            call = "encode_cm<kUseLut>(c, lut)" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c)"
             out.append(f"    if (fam == {fid}) return {call};")
         out.append("    return 0u;")
     out.append("  }")
@@ -494,8 +504,8 @@ def generate(cfg_path):
     out.append("")
     out.append("static bool matches(const mpc_config_pod& cfg) { return spec_pod_equal(cfg, kPod); }")
     out.append("static cudaError_t launch(const mpc_config_pod&, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed,")
-    out.append("                          uint64_t* d_stats, int sm_count, cudaStream_t stream) {")
-    out.append("  return launch_spec<Cfg>(d_lines, n_blocks, d_packed, d_stats, sm_count, stream);")
+    out.append("                          uint64_t* d_stats, const uint8_t* d_row_lut, int sm_count, cudaStream_t stream) {")
+    out.append("  return launch_spec<Cfg>(d_lines, n_blocks, d_packed, d_stats, d_row_lut, sm_count, stream);")
     out.append("}")
     out.append(f"}}  // namespace spec_{name}")
     out.append(f'extern const SpecKernel kSpec_{name} = {{"{name}", spec_{name}::matches, spec_{name}::launch}};')
