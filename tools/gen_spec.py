@@ -228,7 +228,7 @@ def emit_full(m, out):
     """full_<m>: all 32 residue words -> residue sums, canonical row layout c[32]."""
     out.append(f"__device__ __forceinline__ void full_{m.idx}(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq) {{")
     out.append("  uint32_t g[32];")
-    out.append("  sa = 0; sq = 0;")
+    out.append("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one")
     for w in range(W):
         out.append("  { " + m.residue_stmts(w, "r"))
         if w == 0:
@@ -240,10 +240,11 @@ def emit_full(m, out):
                 out.append("    const uint32_t rs = r & 0xffffff00u;")
             else:
                 out.append(f"    const uint32_t rs = (r & 0xffffff00u) | (((x[{rw}] >> {8 * rb}) - (x[{pw}] >> {8 * pb})) & 0xffu);")
-            out.append("    sa += mpcdev::sum_u8x4(rs); sq = __dp4a(rs, rs, sq);")
+            out.append("    sa0 += mpcdev::sum_u8x4(rs); sq0 = __dp4a(rs, rs, sq0);")
         else:
-            out.append("    sa += mpcdev::sum_u8x4(r); sq = __dp4a(r, r, sq);")
+            out.append(f"    sa{w % 4} += mpcdev::sum_u8x4(r); sq{w % 4} = __dp4a(r, r, sq{w % 4});")
         out.append(f"    g[{w}] = {m.g_from_r(w, 'r')}; }}")
+    out.append("  sa = (sa0 + sa1) + (sa2 + sa3); sq = (sq0 + sq1) + (sq2 + sq3);")
     if m.family == "cm":
         cols = m.cols + [None] * (L - len(m.cols))
         for j in range(W):
