@@ -182,3 +182,42 @@ def test_unknown_config_falls_back_to_generic_and_says_so(mpcb):
     assert m.kernel_name() == "generic_warp"
     with pytest.raises(mpcb.MpcError):
         m.set_kernel(2)
+
+
+def test_mixed_dump_fires_every_branch(mpcb):
+    """BASELINE config #3 in miniature: on the hashed mixed dump every cluster is selected (zero, word-same, each
+    predictor, raw fallback), zero rows appear both isolated and in runs, and every row pattern of the common
+    encoder occurs -- checked on the oracle's view of the same blocks, then the GPU must agree bit for bit."""
+    n = 200000
+    blocks = synth("mixed_hashed", 77, 0, n, n)
+    for cfg in ("P6", "E5"):
+        m = mpcb.Mpc(cfg_path(cfg))
+        sizes, sels, st = m.compress(blocks)
+        r = OracleMPC(cfg_path(cfg)).run(blocks)
+        assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
+        if cfg == "P6":
+            assert np.all(st.count > 0), (cfg, st.count)             # every cluster incl. -1 (raw) is hit
+        assert st.hist[0, 8 * 128 + int(m.cfg.enc_bits[0])] > 0       # raw fallback size
+        comp = sizes[sels >= m.cfg.first_predcomp]
+        assert comp.min() < 100 and comp.max() > 900                  # from a handful of rows to nearly raw
+
+
+def test_four_gib_mixed_properties(mpcb):
+    """BASELINE config #3 size (4 GiB, 33 554 432 blocks): totals = sum of per-block results, window = oracle."""
+    import torch
+    cfg = "F4"
+    m = mpcb.Mpc(cfg_path(cfg))
+    n = (4 << 30) // 128
+    d = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    packed = torch.zeros(n, dtype=torch.int16, device="cuda")
+    m.synth_device(d.data_ptr(), 0, n, n, "mixed_hashed", 31337)
+    m.reset()
+    m.submit_device(d.data_ptr(), n, packed.data_ptr())
+    st = m.finish()
+    p = packed.view(torch.int32)  # two packed results per word: sum sizes on the device
+    lo = (p & 0x7FF).to(torch.int64).sum().item() + ((p >> 16) & 0x7FF).to(torch.int64).sum().item()
+    assert st.blocks == n and st.CompressedSize == lo
+    w0, wn = 20_000_000, 30000
+    sizes, sels = mpcb.unpack(packed[w0:w0 + wn].cpu().numpy().view(np.uint16))
+    r = OracleMPC(cfg_path(cfg)).run(synth("mixed_hashed", 31337, w0, wn, n))
+    assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
