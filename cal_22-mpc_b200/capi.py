@@ -59,7 +59,8 @@ SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config
            "mpc_destroy", "mpc_last_error", "mpc_global_error", "mpc_set_kernel", "mpc_kernel_name", "mpc_set_stream",
            "mpc_submit_device", "mpc_submit_host", "mpc_sync", "mpc_stats_device_ptr", "mpc_finish",
            "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version",
-           "mpc_variant_run_device", "mpc_variant_run_host", "mpc_variant_error"]
+           "mpc_variant_run_device", "mpc_variant_run_host", "mpc_variant_error", "mpc_sc2_run_device", "mpc_sc2_run_host",
+           "mpc_sc2_error", "mpc_cpack_run_host"]
 
 
 def lib():
@@ -96,6 +97,10 @@ def lib():
     l.mpc_variant_run_device.argtypes = [C.c_int, C.c_int, vp, u64, C.c_uint32, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
     l.mpc_variant_run_host.argtypes = [C.c_int, C.c_int, vp, u64, C.c_uint32, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
     l.mpc_variant_error.restype = C.c_char_p
+    l.mpc_sc2_run_device.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
+    l.mpc_sc2_run_host.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
+    l.mpc_sc2_error.restype = C.c_char_p
+    l.mpc_cpack_run_host.argtypes = [vp, u64, C.c_uint32, vp, C.POINTER(VariantStats)]
     _LIB = l
     return l
 
@@ -244,6 +249,33 @@ def variant_run(alg, lines=None, device_ptr=None, n_blocks=None, device=0, want_
     if rc != 0:
         raise MpcError(f"variant {alg} failed ({rc}): {lib().mpc_variant_error().decode()}")
     return sizes, st, ms.value
+
+
+def sc2_sampling_lines(loader_rows):
+    """main.cpp:108-114: sampling count from the loader's row count."""
+    return max(10000, min(loader_rows // 100, 1000000))
+
+
+def sc2_run(lines, sampling_lines, device=0, line_size=128):
+    lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, line_size)
+    n = lines.shape[0]
+    sizes = np.zeros(n, dtype=np.uint16)
+    st, ms = VariantStats(), C.c_float()
+    rc = lib().mpc_sc2_run_host(device, lines.ctypes.data, n, line_size, sampling_lines, sizes.ctypes.data, C.byref(st), C.byref(ms))
+    if rc != 0:
+        raise MpcError(f"SC2 failed ({rc}): {lib().mpc_sc2_error().decode()}")
+    return sizes, st, ms.value
+
+
+def cpack_run(lines, line_size=128):
+    lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, line_size)
+    n = lines.shape[0]
+    sizes = np.zeros(n, dtype=np.uint16)
+    st = VariantStats()
+    rc = lib().mpc_cpack_run_host(lines.ctypes.data, n, line_size, sizes.ctypes.data, C.byref(st))
+    if rc != 0:
+        raise MpcError(f"CPACK failed ({rc})")
+    return sizes, st
 
 
 def unpack(packed):

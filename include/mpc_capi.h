@@ -171,6 +171,21 @@ int mpc_variant_run_host(int alg, int device, const uint8_t* h_lines, uint64_t n
                          uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms);
 const char* mpc_variant_error(void);
 
+/* SC2 (Huffman over 32-bit words, SC2.cpp:270-334): device sort + run-length histogram of the first sampling_lines
+ * lines, host tree with the reference's heap rules, device lookup.  sampling_lines is what main.cpp:108-114 derives
+ * from the loader's row count: max(10000, min(rows / 100, 1000000)).  counts[0] = symbols that received a code. */
+int mpc_sc2_run_device(int device, const uint8_t* d_lines, uint64_t n_blocks, uint32_t line_size, uint64_t sampling_lines,
+                       uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms);
+int mpc_sc2_run_host(int device, const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size, uint64_t sampling_lines,
+                     uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms);
+const char* mpc_sc2_error(void);
+
+/* CPACK (CPACK.cpp:7-101): the 16-entry dictionary persists across lines, so the result depends on every earlier word
+ * -- sequential by construction; this entry point runs on the host and is reported as such.
+ * counts = ZZZZ, XXXX, MMMM, MMXX, ZZZX, MMMX (order of m_PatternLength, CPACK.h:119-127). */
+int mpc_cpack_run_host(const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size, uint16_t* h_sizes,
+                       mpc_variant_stats* out);
+
 /* ---- library info ---------------------------------------------------------------------- */
 const char* mpc_version(void);
 

@@ -43,6 +43,27 @@ def oracle_lib():
     return _oracle
 
 
+def oracle_cpack(lines, L=128):
+    lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, L)
+    sizes = np.zeros(lines.shape[0], dtype=np.uint32)
+    counts = np.zeros(8, dtype=np.uint64)
+    l = oracle_lib()
+    l.orc_cpack_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_void_p, C.c_void_p]
+    l.orc_cpack_run.restype = None
+    l.orc_cpack_run(lines.ctypes.data, lines.shape[0], L, sizes.ctypes.data, counts.ctypes.data)
+    return sizes, counts
+
+
+def oracle_sc2(lines, sampling, L=128):
+    lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, L)
+    sizes = np.zeros(lines.shape[0], dtype=np.uint32)
+    l = oracle_lib()
+    l.orc_sc2_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64, C.c_void_p]
+    l.orc_sc2_run.restype = None
+    l.orc_sc2_run(lines.ctypes.data, lines.shape[0], L, sampling, sizes.ctypes.data)
+    return sizes
+
+
 VARIANT_ID = {"BDI": 1, "FPC": 2, "BPC": 3}
 
 

@@ -166,3 +166,146 @@ void orc_variant_run(int alg, const uint8_t* lines, uint64_t n, unsigned L, uint
     if (sizes) sizes[i] = s;
   }
 }
+
+/* ---- CPACK: CPACK.cpp:7-101, pattern lengths CPACK.h:127.  The 16-entry FIFO dictionary (zero-initialised,
+ * CPACK.h:107-113) persists across lines: strictly sequential. ---------------------------------------------------- */
+typedef struct { uint8_t e[16][4]; int head; } orc_cpack_state;
+
+void orc_cpack_init(orc_cpack_state* s) { memset(s, 0, sizeof(*s)); }
+
+/* counts[6]: ZZZZ, XXXX, MMMM, MMXX, ZZZX, MMMX in the order of m_PatternLength (CPACK.h:119-127) */
+unsigned orc_cpack_line(orc_cpack_state* s, const uint8_t* line, unsigned L, uint64_t* counts) {
+  static const unsigned len[6] = {2, 34, 6, 24, 12, 16};
+  unsigned size = 0;
+  for (unsigned i = 0; i < L / 4; i++) {
+    const uint8_t* w = line + 4 * i;
+    int pat = -1;
+    if (w[0] == 0 && w[1] == 0 && w[2] == 0) {
+      pat = (w[3] == 0) ? 0 : 4;
+    } else {
+      for (int j = 0; j < 16 && pat < 0; j++) { /* oldest entry first (deque front), CPACK.cpp:41 */
+        const uint8_t* d = s->e[(s->head + j) & 15];
+        if (w[0] == d[0] && w[1] == d[1]) pat = (w[2] == d[2]) ? ((w[3] == d[3]) ? 2 : 5) : 3;
+      }
+      if (pat < 0) { /* xxxx: push back, pop front (CPACK.cpp:84-93) */
+        pat = 1;
+        memcpy(s->e[s->head], w, 4);
+        s->head = (s->head + 1) & 15;
+      }
+    }
+    size += len[pat];
+    if (counts) counts[pat]++;
+  }
+  return size;
+}
+
+void orc_cpack_run(const uint8_t* lines, uint64_t n, unsigned L, uint32_t* sizes, uint64_t* counts) {
+  orc_cpack_state s;
+  orc_cpack_init(&s);
+  for (uint64_t i = 0; i < n; i++) {
+    unsigned v = orc_cpack_line(&s, lines + i * L, L, counts);
+    if (sizes) sizes[i] = v;
+  }
+}
+
+/* ---- SC2: SC2.cpp:270-334 (sampling, trim to 1024 symbols, tree, lookup), heap SC2.cpp:24-126 --------------------- */
+#include <stdlib.h>
+
+typedef struct orc_node { int64_t symbol; uint64_t freq; struct orc_node *left, *right; } orc_node;
+
+static void heap_swap(orc_node** a, int i, int j) { orc_node* t = a[i]; a[i] = a[j]; a[j] = t; }
+static void heapify(orc_node** a, int size, int index) { /* SC2.cpp:61-84 */
+  int m = index, l = 2 * index + 1, r = 2 * index + 2;
+  if (l <= size - 1 && a[l]->freq < a[m]->freq) m = l;
+  if (r <= size - 1 && a[r]->freq < a[m]->freq) m = r;
+  if (m != index) { heap_swap(a, index, m); heapify(a, size, m); }
+}
+static void leaf_depths(orc_node* nd, int depth, uint32_t* syms, uint8_t* lens, int* k) { /* SC2.cpp:150-162 */
+  if (!nd->left && !nd->right) { syms[*k] = (uint32_t)nd->symbol; lens[*k] = (uint8_t)depth; (*k)++; return; }
+  leaf_depths(nd->left, depth + 1, syms, lens, k);
+  leaf_depths(nd->right, depth + 1, syms, lens, k);
+}
+static int cmp_u32(const void* a, const void* b) { uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b; return x < y ? -1 : x > y; }
+typedef struct { uint32_t sym; uint64_t freq; } orc_sf;
+static int cmp_freq_sym(const void* a, const void* b) { /* huffman::cmp, SC2.cpp:257-261 */
+  const orc_sf *x = a, *y = b;
+  if (x->freq == y->freq) return x->sym < y->sym ? -1 : x->sym > y->sym;
+  return x->freq < y->freq ? -1 : 1;
+}
+static int cmp_sym(const void* a, const void* b) { const orc_sf *x = a, *y = b; return x->sym < y->sym ? -1 : x->sym > y->sym; }
+typedef struct { uint32_t sym; uint8_t len; } orc_code;
+static int cmp_code(const void* a, const void* b) { const orc_code *x = a, *y = b; return x->sym < y->sym ? -1 : x->sym > y->sym; }
+
+/* Builds the code-length table from the words of the first `sampling` lines.  Returns the number of symbols. */
+int orc_sc2_table(const uint8_t* lines, uint64_t sampling, unsigned L, uint32_t* out_syms, uint8_t* out_lens) {
+  const uint64_t nw = sampling * (L / 4);
+  uint32_t* w = (uint32_t*)malloc(nw * 4 + 4);
+  memcpy(w, lines, nw * 4);
+  qsort(w, nw, 4, cmp_u32);
+  orc_sf* sf = (orc_sf*)malloc((nw + 1) * sizeof(orc_sf));
+  uint64_t d = 0;
+  for (uint64_t i = 0; i < nw;) {
+    uint64_t j = i;
+    while (j < nw && w[j] == w[i]) j++;
+    sf[d].sym = w[i]; sf[d].freq = j - i; d++;
+    i = j;
+  }
+  free(w);
+  if (d > 1024) { /* drop the least frequent (ties: smaller symbol first) until 1024 remain, SC2.cpp:294-307 */
+    qsort(sf, d, sizeof(orc_sf), cmp_freq_sym);
+    memmove(sf, sf + (d - 1024), 1024 * sizeof(orc_sf));
+    d = 1024;
+    qsort(sf, d, sizeof(orc_sf), cmp_sym); /* std::map order */
+  }
+  if (d == 0) { free(sf); return 0; }
+  orc_node** heap = (orc_node**)malloc(1025 * sizeof(orc_node*));
+  orc_node* pool = (orc_node*)calloc(2 * 1024 + 2, sizeof(orc_node));
+  int np = 0, size = (int)d;
+  for (int i = 0; i < size; i++) { pool[np].symbol = sf[i].sym; pool[np].freq = sf[i].freq; heap[i] = &pool[np++]; }
+  for (int i = size / 2 - 1; i >= 0; i--) heapify(heap, size, i); /* buildHeap, SC2.cpp:49-59 */
+  while (size > 1) { /* BuildHuffmanTree, SC2.cpp:138-148 */
+    orc_node* l = heap[0]; heap_swap(heap, 0, size - 1); size--; heapify(heap, size, 0);
+    orc_node* r = heap[0]; heap_swap(heap, 0, size - 1); size--; heapify(heap, size, 0);
+    orc_node* nn = &pool[np++];
+    nn->symbol = -1; nn->freq = l->freq + r->freq; nn->left = l; nn->right = r;
+    heap[size++] = nn; /* AddNode, SC2.cpp:97-111 */
+    for (int i = size - 1; i > 0;) {
+      int p = (i + 1) / 2 - 1; /* ceil(i / 2) - 1 */
+      if (!(heap[p]->freq > heap[i]->freq)) break;
+      heap_swap(heap, i, p);
+      i = p;
+    }
+  }
+  int k = 0;
+  leaf_depths(heap[0], 0, out_syms, out_lens, &k);
+  orc_code* codes = (orc_code*)malloc((size_t)k * sizeof(orc_code));
+  for (int i = 0; i < k; i++) { codes[i].sym = out_syms[i]; codes[i].len = out_lens[i]; }
+  qsort(codes, (size_t)k, sizeof(orc_code), cmp_code);
+  for (int i = 0; i < k; i++) { out_syms[i] = codes[i].sym; out_lens[i] = codes[i].len; }
+  free(codes); free(pool); free(heap); free(sf);
+  return k;
+}
+
+/* sizes per line.  `sampling` = number of sampling lines (main.cpp:108-114 computes it from the loader's row count). */
+void orc_sc2_run(const uint8_t* lines, uint64_t n, unsigned L, uint64_t sampling, uint32_t* sizes) {
+  const unsigned W = L / 4;
+  uint32_t syms[1024];
+  uint8_t lens[1024];
+  int k = -1;
+  for (uint64_t i = 0; i < n; i++) {
+    unsigned s = 0;
+    if (i < sampling) {
+      s = 33 * W;
+    } else {
+      if (k < 0) k = orc_sc2_table(lines, sampling, L, syms, lens);
+      for (unsigned j = 0; j < W; j++) {
+        uint32_t v;
+        memcpy(&v, lines + i * L + 4 * j, 4);
+        int lo = 0, hi = k - 1, hit = -1;
+        while (lo <= hi) { int mid = (lo + hi) / 2; if (syms[mid] == v) { hit = mid; break; } if (syms[mid] < v) lo = mid + 1; else hi = mid - 1; }
+        s += hit >= 0 ? lens[hit] : 33;
+      }
+    }
+    sizes[i] = s;
+  }
+}

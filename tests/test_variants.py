@@ -91,3 +91,53 @@ def test_gpu_variants_at_scale_are_consistent(mpcb):
         sizes, _, _ = mpcb.variant_run(alg, d[w0 * 128:(w0 + 5000) * 128].cpu().numpy())
         assert np.array_equal(sizes.astype(np.uint32), want)
         print(alg, "GB/s", n * 128 / ms / 1e6, "ratio", whole.original_bits / whole.compressed_bits)
+
+
+# ---- CPACK (host, sequential) and SC2 (GPU histogram + host tree + GPU lookup) -----------------------------------------
+KAT_CPACK = [64, 220, 1056, 1088, 1088, 668, 128, 516, 192]  # SURVEY.md section 8c, this order in one process
+
+
+def _mixed(n, seed=3):
+    rng = np.random.default_rng(seed)
+    return np.concatenate([kat_blocks(), synth("mixed_hashed", seed, 0, n, n), random_blocks(rng, n // 6)])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_cpack_sc2_oracles_match_reference():
+    from oracle.bridge import oracle_cpack, oracle_sc2
+    d = _mixed(30000)
+    sizes, counts = oracle_cpack(d)
+    assert sizes[:9].tolist() == KAT_CPACK
+    rs, _ = RefCompressor("CPACK", None, 128).compress(d)
+    assert np.array_equal(sizes, rs)
+    for S in (10000, 20000, 300):
+        ref = RefCompressor("SC2", None, 128, S)
+        rs, _ = ref.compress(d)
+        assert np.array_equal(oracle_sc2(d, S), rs), S
+    few = synth("sparse_i32", 3, 0, 40000, 40000)  # fewer than 1024 distinct symbols: no trimming
+    rs, _ = RefCompressor("SC2", None, 128, 10000).compress(few)
+    assert np.array_equal(oracle_sc2(few, 10000), rs)
+
+
+def test_cpack_host_matches_oracle(mpcb):
+    from oracle.bridge import oracle_cpack
+    d = _mixed(20000)
+    sizes, st = mpcb.cpack_run(d)
+    want, counts = oracle_cpack(d)
+    assert np.array_equal(sizes.astype(np.uint32), want)
+    assert st.compressed_bits == int(want.astype(np.uint64).sum()) and st.blocks == d.shape[0]
+    assert np.array_equal(np.array(st.counts[:6], dtype=np.uint64), counts[:6])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,S", [("mixed_hashed", 60000, 10000), ("mixed_hashed", 60000, 25000), ("sparse_i32", 40000, 10000),
+                                      ("random", 30000, 10000), ("zero", 20000, 10000), ("mixed_hashed", 5000, 10000)])
+def test_sc2_gpu_matches_oracle(mpcb, kind, n, S):
+    from oracle.bridge import oracle_sc2
+    d = synth(kind, 17, 0, n, n)
+    sizes, st, ms = mpcb.sc2_run(d, S)
+    want = oracle_sc2(d, S)
+    bad = np.nonzero(sizes.astype(np.uint32) != want)[0]
+    assert bad.size == 0, (bad[:5], sizes[bad[:5]], want[bad[:5]])
+    assert st.compressed_bits == int(want.astype(np.uint64).sum()) and st.original_bits == n * 1024
+    assert mpcb.sc2_sampling_lines(n + 1) == max(10000, min((n + 1) // 100, 1000000))  # main.cpp:108-114
