@@ -12,12 +12,13 @@
 #include <vector>
 
 #include "compressor/VPC.h"
+#include "compressor/Variants.h"
 #include "loader/LoaderNPY.h"
 #include "utils.h"
 
 static const char* kHelp =
     "\nUsage:\n  Compressor [OPTION...]\n\n"
-    "  -a, --algorithm arg  Compression algorithm [VPC]. Default=VPC\n"
+    "  -a, --algorithm arg  Compression algorithm [VPC/FPC/BDI/BPC/CPACK/SC2]. Default=VPC\n"
     "  -i, --input arg      Input memory dump path. Supported extensions: .npy\n"
     "  -c, --config arg     Config file path (.json).\n"
     "  -o, --output arg     Output directory path\n"
@@ -66,8 +67,11 @@ int main(int argc, char** argv) {
   comp::Compressor* compressor = nullptr;
   if (algorithm == "VPC") {
     compressor = new comp::VPC(configPath, gpus, kernel);  // main.cpp:88-91
+  } else if (algorithm == "BDI" || algorithm == "FPC" || algorithm == "BPC" || algorithm == "CPACK" || algorithm == "SC2") {
+    compressor = new comp::VariantCompressor(algorithm, lineSize, loader->GetNumLines());  // main.cpp:92-116
   } else {
-    printf("Invalid name of algorithm: \"%s\" (this build implements VPC = MPC)\n", algorithm.c_str());
+    // PATTERN (analysis tool, ratio always 0) and VIEWER are outside the compression path
+    printf("Invalid name of algorithm: \"%s\" (this build implements VPC, BDI, FPC, BPC, CPACK, SC2)\n", algorithm.c_str());
     return 1;
   }
 
@@ -89,7 +93,7 @@ int main(int argc, char** argv) {
   replaceAll(appName, ".txt", "");
   std::string workloadName = benchmarkName + "_" + appName;
   std::cout << "comp.ratio: " << formatDouble(compStat->CompRatio) << std::endl;  // main.cpp:158
-  if (timing) {
+  if (timing && algorithm == "VPC") {
     comp::VPC* v = static_cast<comp::VPC*>(compressor);
     double wall = std::chrono::duration<double>(t1 - t0).count();
     fprintf(stderr, "kernel %s: device %.3f ms, wall %.3f s, %llu blocks of %u B\n", v->KernelName(), v->KernelMs(), wall,

@@ -114,3 +114,21 @@ def test_bin_run_walks_the_dataset_like_the_reference(tmp_path, golden):
     # single-line reference path still works: CompressLine through the same library
     want = golden["P6_sizes"][:100].astype(np.uint64).sum()
     assert int(rows[2].split(",")[2]) == int(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["BDI", "FPC", "BPC", "CPACK", "SC2"])
+def test_variant_csv_bytes_equal_reference(tmp_path, alg):
+    """BASELINE config #5 through the drop-in CLI: same CSV row and stdout as the reference binary on the same dump
+    (tests/golden/cli_<ALG>_*, generated by tools/make_golden.py from the unmodified reference)."""
+    _build()
+    from tools.gen_dump import synth
+    ds = tmp_path / "ds"
+    out = tmp_path / "out"
+    ds.mkdir()
+    out.mkdir()
+    np.save(ds / "variants_set.npy", np.concatenate([synth("mixed_hashed", 555, 0, 12000, 12000), np.zeros((1, 128), np.uint8)]))
+    r = subprocess.run([BIN, "-a", alg, "-i", str(ds / "variants_set.npy"), "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout == open(os.path.join(GOLD, f"cli_{alg}_stdout.txt")).read()
+    assert open(out / f"{alg}_results.csv").read() == open(os.path.join(GOLD, f"cli_{alg}_results.csv")).read()

@@ -103,6 +103,20 @@ def main():
             with open(os.path.join(gold, f"cli_{cfg}_stdout.txt"), "w") as g:
                 g.write(stdout)
             print(cfg, "cli:", stdout.strip())
+        # secondary variants (config #5) through the reference CLI, on a 12 001-row dump so that SC2 leaves its
+        # 10 000-line sampling phase (main.cpp:108-114); the dump is synth("mixed_hashed", 555, 0, 12000, 12000) + 1 row
+        np.save(os.path.join(ds, "variants_set.npy"),
+                np.concatenate([synth("mixed_hashed", 555, 0, 12000, 12000), np.zeros((1, 128), np.uint8)]))
+        for alg in ("BDI", "FPC", "BPC", "CPACK", "SC2"):
+            outdir = os.path.join(tmp, "out_" + alg)
+            os.makedirs(outdir)
+            r = subprocess.run([REF_BIN, "-a", alg, "-i", os.path.join(ds, "variants_set.npy"), "-o", outdir],
+                               capture_output=True, text=True, check=True)
+            with open(os.path.join(outdir, f"{alg}_results.csv")) as f, open(os.path.join(gold, f"cli_{alg}_results.csv"), "w") as g:
+                g.write(f.read())
+            with open(os.path.join(gold, f"cli_{alg}_stdout.txt"), "w") as g:
+                g.write(r.stdout)
+            print(alg, "cli:", r.stdout.strip())
 
 
 if __name__ == "__main__":
