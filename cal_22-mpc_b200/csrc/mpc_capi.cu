@@ -184,15 +184,15 @@ int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out) {
   const size_t gbytes = sizeof(mpc::GenericModule) * (size_t)(ctx->gparams.num_predcomp > 0 ? ctx->gparams.num_predcomp : 1);
   MPC_CREATE_CUDA(cudaMalloc(&ctx->d_gmods, gbytes));
   MPC_CREATE_CUDA(cudaMemcpyAsync(ctx->d_gmods, gm.data(), gbytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->spec = mpc::find_spec_kernel(ctx->cfg);
   {
     std::vector<uint8_t> lut(65536);
-    mpc::build_row_cost_lut(lut.data());
+    mpc::build_row_cost_lut(lut.data(), ctx->spec ? ctx->spec->lut_xor : 0);
     MPC_CREATE_CUDA(cudaMalloc(&ctx->d_row_lut, lut.size()));
     MPC_CREATE_CUDA(cudaMemcpy(ctx->d_row_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
   }
   MPC_CREATE_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef MPC_CREATE_CUDA
-  ctx->spec = mpc::find_spec_kernel(ctx->cfg);
   refresh_kernel_name(ctx);
   *out = ctx;
   return MPC_OK;

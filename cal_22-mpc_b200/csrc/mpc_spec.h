@@ -13,10 +13,11 @@ struct SpecKernel {
   bool (*matches)(const mpc_config_pod& cfg);
   cudaError_t (*launch)(const mpc_config_pod& cfg, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed,
                         uint64_t* d_stats, const uint8_t* d_row_lut, int sm_count, cudaStream_t stream);
+  int lut_xor;  // which row-cost table the kernel expects (0 plain, 1 consecutive-XOR folded in, 2 first-plane-XOR folded in)
 };
 
 // 65 536-entry table of the common encoder's cost of a non-zero 16-bit scan row (0 for the zero row), FPCModule.cpp:47-66
-void build_row_cost_lut(uint8_t* lut);
+void build_row_cost_lut(uint8_t* lut, int lut_xor);
 
 // true when the two configs describe the same computation (fields the kernels depend on)
 bool spec_pod_equal(const mpc_config_pod& a, const mpc_config_pod& b);

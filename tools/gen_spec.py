@@ -224,8 +224,12 @@ class Module:
 # ---------------------------------------------------------------------------------------------------------------
 # emission
 # ---------------------------------------------------------------------------------------------------------------
-def emit_full(m, out):
-    """full_<m>: all 32 residue words -> residue sums, canonical row layout c[32]."""
+def emit_full(m, out, lut_xor=0):
+    """full_<m>: all 32 residue words -> residue sums, canonical row layout c[32].
+    lut_xor != 0 (column-major modules only): the row-cost table is indexed with the residue bytes BEFORE the XOR
+    stage -- the stage is a per-byte bijection (Gray code / conditional complement), so it is folded into the table
+    and disappears from the kernel; only the root byte, which the XOR stage skips (XORModule.cpp:12), is run
+    through the inverse map so that the table maps it back to itself."""
     out.append(f"__device__ __forceinline__ void full_{m.idx}(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq) {{")
     out.append("  uint32_t g[32];")
     out.append("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one")
@@ -243,7 +247,14 @@ def emit_full(m, out):
             out.append("    sa0 += mpcdev::sum_u8x4(rs); sq0 = __dp4a(rs, rs, sq0);")
         else:
             out.append(f"    sa{w % 4} += mpcdev::sum_u8x4(r); sq{w % 4} = __dp4a(r, r, sq{w % 4});")
-        out.append(f"    g[{w}] = {m.g_from_r(w, 'r')}; }}")
+        if lut_xor and m.family == "cm":
+            if w == 0:
+                inv = "inv_gray8" if lut_xor == 1 else "inv_first8"
+                out.append(f"    g[0] = (r & 0xffffff00u) | {inv}(r & 0xffu); }}")
+            else:
+                out.append(f"    g[{w}] = r; }}")
+        else:
+            out.append(f"    g[{w}] = {m.g_from_r(w, 'r')}; }}")
     out.append("  sa = (sa0 + sa1) + (sa2 + sa3); sq = (sq0 + sq1) + (sq2 + sq3);")
     if m.family == "cm":
         cols = m.cols + [None] * (L - len(m.cols))
@@ -432,6 +443,14 @@ def generate(cfg_path):
     out.append("using namespace mpc::spec;")
     out.append("template <class F> __device__ __forceinline__ uint32_t shiftmix(uint32_t p, F f) { return f(p); }")
     out.append("")
+    cm_mods = [m for m in mods if m.family == "cm"]
+    lut_on = bool(cm_mods) and os.environ.get("MPC_SPEC_LUT", "1") != "0"
+    lut_xor = 0
+    if lut_on and os.environ.get("MPC_SPEC_LUTXOR", "1") != "0":
+        if all(m.cxor for m in cm_mods):
+            lut_xor = 1
+        elif not any(m.cxor for m in cm_mods):
+            lut_xor = 2
     for m in mods:
         out.append(f"// ---- module {m.idx}: {m.pname}, root {m.root}, {'consecutive' if m.cxor else 'first-plane'} XOR, "
                    f"{'column' if m.family == 'cm' else 'plane'}-major scan ----")
@@ -439,7 +458,7 @@ def generate(cfg_path):
             emit_score_cm(m, out)
         else:
             emit_score_pm(m, out)
-        emit_full(m, out)
+        emit_full(m, out, lut_xor)
         out.append("")
     out.append("struct Cfg {")
     out.append(f"  static constexpr int kNumModules = {n};")
@@ -457,6 +476,9 @@ def generate(cfg_path):
         min_ctas = 1
     out.append(f"  static constexpr int kWarps = {warps};")
     out.append(f"  static constexpr bool kUseLut = {'true' if use_lut else 'false'};  // shared-memory row-cost table (column-major modules)")
+    skip = os.environ.get("MPC_SPEC_SKIP", "0" if use_lut else "1") != "0"
+    out.append(f"  static constexpr bool kSkipZeroGroups = {'true' if skip else 'false'};  // branch around groups of eight zero rows in the encoder")
+    out.append(f"  static constexpr int kLutXor = {lut_xor if use_lut else 0};  // 0: table indexed by scan rows; 1 / 2: XOR stage (consecutive / first-plane) folded into the table")
     out.append(f"  static constexpr int kMinCtasPerSm = {min_ctas};  // __launch_bounds__: register budget 65536 / (threads * CTAs)")
     out.append("  __device__ static __forceinline__ uint32_t enc(int k) {  // encoding bits of cluster k-1, VPC.cpp:102-117")
     out.append("    switch (k) {")
@@ -491,10 +513,10 @@ def generate(cfg_path):
     if len(fams) == 1:
         fam, sels = fams[0]
         out.append("    (void)fam;")
-        out.append("    return " + ("encode_cm<kUseLut>(c, lut);" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c);"))
+        out.append("    return " + ("encode_cm<kUseLut, kSkipZeroGroups>(c, lut);" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c);"))
     else:
         for fid, (fam, sels) in enumerate(fams):
-            call = "encode_cm<kUseLut>(c, lut)" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c)"
+            call = "encode_cm<kUseLut, kSkipZeroGroups>(c, lut)" if fam == "cm" else f"encode_pm<0x{sels[0]:04x}u, 0x{sels[1]:04x}u>(c)"
             out.append(f"    if (fam == {fid}) return {call};")
         out.append("    return 0u;")
     out.append("  }")
@@ -509,7 +531,7 @@ def generate(cfg_path):
     out.append("  return launch_spec<Cfg>(d_lines, n_blocks, d_packed, d_stats, d_row_lut, sm_count, stream);")
     out.append("}")
     out.append(f"}}  // namespace spec_{name}")
-    out.append(f'extern const SpecKernel kSpec_{name} = {{"{name}", spec_{name}::matches, spec_{name}::launch}};')
+    out.append(f'extern const SpecKernel kSpec_{name} = {{"{name}", spec_{name}::matches, spec_{name}::launch, spec_{name}::Cfg::kLutXor}};')
     out.append("}  // namespace mpc")
     os.makedirs(OUTDIR, exist_ok=True)
     path = os.path.join(OUTDIR, f"spec_{name}.cu")
