@@ -54,6 +54,25 @@ MPC_HD uint32_t shr_fma(uint32_t x, int n) {
   return x >> n;
 #endif
 }
+// a * k + b on the FMA pipe; `volatile` keeps ptxas from folding the result back into ALU-pipe forms (LEA.HI, IADD3)
+MPC_HD uint32_t mad_fma(uint32_t a, uint32_t k, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(k), "r"(b));
+  return d;
+#else
+  return a * k + b;
+#endif
+}
+MPC_HD uint32_t shr_fma_opaque(uint32_t x, int n) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(1u << (32 - n)));
+  return d;
+#else
+  return x >> n;
+#endif
+}
 // a - b issued on the FMA pipe (IMAD) instead of the ALU pipe (IADD3)
 MPC_HD uint32_t sub_fma(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -143,6 +162,14 @@ MPC_HD uint32_t sum_u8x4(uint32_t r) {
   return __vsadu4(r, 0u);
 #else
   return (r & 0xff) + ((r >> 8) & 0xff) + ((r >> 16) & 0xff) + (r >> 24);
+#endif
+}
+// acc + sum of the 4 bytes as a dot product with ones (IDP.4A), off the ALU pipe
+MPC_HD uint32_t sum_u8x4_acc(uint32_t r, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+  return __dp4a(r, 0x01010101u, acc);
+#else
+  return acc + (r & 0xff) + ((r >> 8) & 0xff) + ((r >> 16) & 0xff) + (r >> 24);
 #endif
 }
 MPC_HD uint32_t sumsq_u8x4(uint32_t r) {

@@ -244,9 +244,9 @@ def emit_full(m, out, lut_xor=0):
                 out.append("    const uint32_t rs = r & 0xffffff00u;")
             else:
                 out.append(f"    const uint32_t rs = (r & 0xffffff00u) | (((x[{rw}] >> {8 * rb}) - (x[{pw}] >> {8 * pb})) & 0xffu);")
-            out.append("    sa0 += mpcdev::sum_u8x4(rs); sq0 = __dp4a(rs, rs, sq0);")
+            out.append("    sa0 = mpcdev::sum_u8x4_acc(rs, sa0); sq0 = __dp4a(rs, rs, sq0);")
         else:
-            out.append(f"    sa{w % 4} += mpcdev::sum_u8x4(r); sq{w % 4} = __dp4a(r, r, sq{w % 4});")
+            out.append(f"    sa{w % 4} = mpcdev::sum_u8x4_acc(r, sa{w % 4}); sq{w % 4} = __dp4a(r, r, sq{w % 4});")
         if lut_xor and m.family == "cm":
             if w == 0:
                 inv = "inv_gray8" if lut_xor == 1 else "inv_first8"
