@@ -195,10 +195,19 @@ class Module:
             return f"shiftmix({base}, [](uint32_t p) {{ return {' | '.join(terms)}; }})"
         return base
 
-    def residue_stmts(self, w, name):
-        """C++ statements defining `const uint32_t <name>` = residue word w (before the XOR stage)."""
+    def residue_stmts(self, w, name, shared_low=False):
+        """C++ statements defining `const uint32_t <name>` = residue word w (before the XOR stage).
+        shared_low: both operands are plain line words and `al[i]` = x[i] & 0x7f7f7f7f is available -- the low-7-bit
+        halves of the SWAR subtract are then shared between the word's role as minuend and as prediction."""
         xe = gather_expr("x", self.xsrc[4 * w:4 * w + 4])
-        e = f"sub_u8x4({xe}, {self.pred_expr(w)})"
+        pe = self.pred_expr(w)
+        import re as _re
+        mx, mp = _re.fullmatch(r"x\[(\d+)\]", xe), _re.fullmatch(r"x\[(\d+)\]", pe)
+        if shared_low and mx and mp:
+            a, b = mx.group(1), mp.group(1)
+            e = f"sub_u8x4_shared(x[{a}], x[{b}], al[{a}], al[{b}])"
+        else:
+            e = f"sub_u8x4({xe}, {pe})"
         if w == 0:
             rw, rb = self.root // 4, self.root % 4
             rootbyte = f"(x[{rw}] & 0xffu)" if rb == 0 else f"((x[{rw}] >> {8 * rb}) & 0xffu)"
@@ -233,8 +242,11 @@ def emit_full(m, out, lut_xor=0):
     out.append(f"__device__ __forceinline__ void full_{m.idx}(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq) {{")
     out.append("  uint32_t g[32];")
     out.append("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one")
+    out.append("  uint32_t al[32];")
+    out.append("#pragma unroll")
+    out.append("  for (int i = 0; i < 32; i++) al[i] = x[i] & 0x7f7f7f7fu;  // only the words a plain-copy predictor uses survive")
     for w in range(W):
-        out.append("  { " + m.residue_stmts(w, "r"))
+        out.append("  { " + m.residue_stmts(w, "r", shared_low=True))
         if w == 0:
             # MAE/MSE run over all line positions (ResidueModule.cpp:43-73): the residue line holds the root byte
             # itself at position 0, the statistics hold line[root] - predicted[root] instead
