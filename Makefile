@@ -14,13 +14,16 @@ SPEC_CFGS := P6 F4 Z1 E5
 SPEC_SRCS := $(foreach c,$(SPEC_CFGS),$(CSRC)/spec/spec_$(c).cu)
 CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_variants.cu $(CSRC)/mpc_sc2.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu $(SPEC_SRCS)
 CU_OBJS  := $(CU_SRCS:.cu=.o)
-CC_OBJS  := $(CSRC)/mpc_config.o
+CC_OBJS  := $(CSRC)/mpc_config.o $(CSRC)/mpc_specgen.o
 
 all: $(LIB) compressor oracle
 
-# config compiler: one specialised schedule per shipped config (generated sources are committed)
-$(CSRC)/spec/.stamp: tools/gen_spec.py $(foreach c,$(SPEC_CFGS),configs/$(c).json)
-	python tools/gen_spec.py $(foreach c,$(SPEC_CFGS),configs/$(c).json)
+# config compiler (csrc/mpc_specgen.cpp): one specialised schedule per shipped config; generated sources are committed
+tools/specgen: tools/specgen_main.cpp $(CSRC)/mpc_specgen.cpp $(CSRC)/mpc_specgen.h $(CSRC)/mpc_config.cpp include/mpc_capi.h
+	$(CXX) -O1 -std=c++17 -Iinclude -I$(CSRC) tools/specgen_main.cpp $(CSRC)/mpc_specgen.cpp $(CSRC)/mpc_config.cpp -o $@
+$(CSRC)/spec/.stamp: tools/specgen $(foreach c,$(SPEC_CFGS),configs/$(c).json)
+	@mkdir -p $(CSRC)/spec
+	tools/specgen $(CSRC)/spec $(foreach c,$(SPEC_CFGS),configs/$(c).json)
 	@touch $@
 $(SPEC_SRCS) $(CSRC)/spec/spec_list.inc: $(CSRC)/spec/.stamp
 
@@ -53,7 +56,7 @@ sass: $(LIB)
 	cuobjdump -sass $(LIB) > profiles/libmpc_b200.sass
 
 clean:
-	rm -f $(CSRC)/*.o $(CSRC)/spec/*.o $(LIB) bin/compressor
+	rm -f $(CSRC)/*.o $(CSRC)/spec/*.o $(LIB) bin/compressor tools/specgen
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean sass compressor

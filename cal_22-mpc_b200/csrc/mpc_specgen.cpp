@@ -1,0 +1,619 @@
+// Config compiler for the specialised (thread-per-block) MPC kernel.
+//
+// Turns a flattened config (mpc_config_pod, i.e. what VPC::parseConfig reads, reference VPC.cpp:72-330) into the
+// source of a straight-line schedule over the hand-written primitives of mpc_spec.cuh, with every table folded into
+// immediates:
+//   * predictor byte gathers (PredictorModule.cpp:37-173) and the root-first residue order (ResidueModule.cpp:26-39)
+//     become PRMTs with constant selectors or plain register renaming,
+//   * DiffTable bytes / WeightTable shift distances become immediate operands,
+//   * the scan permutation (ScanModule.cpp:14-20) is recognised as column-major (a scan row = two residue bytes) or
+//     plane-major (a scan row = one bit plane of 16 bytes); column-major modules are scored lazily, row by row, and
+//     stop at their first non-zero row (VPC.cpp:378-387).
+// The same generator serves the ahead-of-time build (tools/specgen -> csrc/spec/spec_<name>.cu, compiled by nvcc)
+// and the run-time path (mpc_jit.cpp: NVRTC at mpc_create for configs that were not compiled in).
+// Eligible: lineSize 128 and every PredComp scan table column-major or plane-major; everything else stays on the
+// generic warp-per-block kernel.
+#include "mpc_specgen.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace mpc {
+namespace {
+
+constexpr int L = 128;
+constexpr int W = 32;
+
+std::string fmt(const char* f, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, f);
+  int n = vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  if (n < (int)sizeof(buf)) return std::string(buf, (size_t)std::max(n, 0));
+  std::string big((size_t)n + 1, '\0');
+  va_start(ap, f);
+  vsnprintf(&big[0], big.size(), f, ap);
+  va_end(ap);
+  big.resize((size_t)n);
+  return big;
+}
+
+std::string join(const std::vector<std::string>& v, const char* sep) {
+  std::string s;
+  for (size_t i = 0; i < v.size(); i++) {
+    if (i) s += sep;
+    s += v[i];
+  }
+  return s;
+}
+
+// ---- byte-gather planning ---------------------------------------------------------------------------------------
+// Expression for a 32-bit word whose byte q is byte srcs[q] of the 128-byte array `arr` (available as arr[0..31]),
+// or zero when srcs[q] < 0.
+std::string gather_expr(const std::string& arr, const int (&srcs)[4]) {
+  bool any = false;
+  for (int s : srcs) any |= (s >= 0);
+  if (!any) return "0u";
+  std::vector<int> words;
+  for (int s : srcs)
+    if (s >= 0 && std::find(words.begin(), words.end(), s / 4) == words.end()) words.push_back(s / 4);
+  uint32_t mask = 0;
+  for (int q = 0; q < 4; q++)
+    if (srcs[q] >= 0) mask |= 0xFFu << (8 * q);
+  auto w = [&](int i) { return fmt("%s[%d]", arr.c_str(), i); };
+  auto finish = [&](const std::string& e) { return mask == 0xFFFFFFFFu ? e : fmt("(%s & 0x%08xu)", e.c_str(), mask); };
+  bool identity = (words.size() == 1);
+  for (int q = 0; q < 4 && identity; q++)
+    if (srcs[q] >= 0 && srcs[q] % 4 != q) identity = false;
+  if (identity) return finish(w(words[0]));
+  if (words.size() <= 2) {
+    const int a = words[0], b = words.size() == 2 ? words[1] : words[0];
+    unsigned sel = 0;
+    for (int q = 0; q < 4; q++) {
+      unsigned nib = 0;
+      if (srcs[q] >= 0) nib = (unsigned)(srcs[q] % 4) + (srcs[q] / 4 == a ? 0u : 4u);
+      sel |= nib << (4 * q);
+    }
+    return finish(fmt("prmt(%s, %s, 0x%04xu)", w(a).c_str(), w(b).c_str(), sel));
+  }
+  // three or four source words: two partial gathers merged by a third PRMT
+  std::vector<int> first(words.begin(), words.begin() + 2), second(words.begin() + 2, words.end());
+  auto in = [](const std::vector<int>& ws, int word) { return std::find(ws.begin(), ws.end(), word) != ws.end(); };
+  auto partial = [&](const std::vector<int>& ws) {
+    const int a = ws[0], b = ws.size() == 2 ? ws[1] : ws[0];
+    unsigned sel = 0;
+    for (int q = 0; q < 4; q++) {
+      unsigned nib = 0;
+      if (srcs[q] >= 0 && in(ws, srcs[q] / 4)) nib = (unsigned)(srcs[q] % 4) + (srcs[q] / 4 == a ? 0u : 4u);
+      sel |= nib << (4 * q);
+    }
+    if (ws.size() == 1 && sel == 0x3210u) return w(a);
+    return fmt("prmt(%s, %s, 0x%04xu)", w(a).c_str(), w(b).c_str(), sel);
+  };
+  unsigned sel = 0;
+  for (int q = 0; q < 4; q++) {
+    const unsigned nib = (srcs[q] < 0 || in(first, srcs[q] / 4)) ? (unsigned)q : 4u + (unsigned)q;
+    sel |= nib << (4 * q);
+  }
+  return finish(fmt("prmt(%s, %s, 0x%04xu)", partial(first).c_str(), partial(second).c_str(), sel));
+}
+
+// ---- module model --------------------------------------------------------------------------------------------------
+struct Module {
+  int idx = 0;
+  int predictor = 0, root = 0;
+  bool cxor = false;
+  int xsrc[L], psrc[L], pval[L];
+  enum Op { kNone, kAdd, kShift } op = kNone;
+  int root_pred = 0;
+  enum Family { kCm, kPm } family = kCm;
+  std::vector<int> cols;  // scan order (cm: one entry per column group; pm: the 128 columns of a plane group)
+  int rho[8] = {0, 1, 2, 3, 4, 5, 6, 7};  // pm: plane scanned by plane group p
+
+  bool rho_identity() const {
+    for (int p = 0; p < 8; p++)
+      if (rho[p] != p) return false;
+    return true;
+  }
+
+  bool init(int index, const mpc_module_pod& m, std::string* why) {
+    idx = index;
+    predictor = m.predictor;
+    root = m.root;
+    cxor = m.consecutive_xor != 0;
+    if (predictor == MPC_PRED_CONSEC && root != 0) { *why = "Consecutive predictor with root != 0"; return false; }
+    int tperm[L], t = 0;
+    for (int plane = 3; plane >= 0; plane--)
+      for (int i = plane; i < L; i += 4) tperm[t++] = i;
+    // source tables in residue order (same construction as build_generic_tables, mpc_generic.cu)
+    for (int j = 0; j < L; j++) {
+      const int i = (j == 0) ? root : (j <= root ? j - 1 : j);
+      xsrc[j] = i;
+      int ps = root, pv = 0;
+      switch (predictor) {
+        case MPC_PRED_ONE: ps = root; break;
+        case MPC_PRED_CONSEC: ps = tperm[i > 0 ? i - 1 : 0]; break;
+        case MPC_PRED_DIFF: ps = m.base[i]; pv = m.diff[i]; break;
+        case MPC_PRED_WEIGHT: ps = m.base[i]; pv = (i != root) ? (int)m.shift[i] : 0; break;
+        default: *why = "unknown predictor"; return false;
+      }
+      if (j == 0) { ps = root; pv = 0; }
+      if (ps < 0 || ps >= L) { *why = "base index outside the line"; return false; }
+      psrc[j] = ps;
+      pval[j] = pv;
+    }
+    op = predictor == MPC_PRED_DIFF ? kAdd : (predictor == MPC_PRED_WEIGHT ? kShift : kNone);
+    root_pred = (predictor == MPC_PRED_CONSEC) ? tperm[root] : root;
+    // ---- scan family ----
+    const int T = m.table_size;
+    const uint8_t* rows = m.scan_row;
+    const uint8_t* cs = m.scan_col;
+    bool cm = (T % 8 == 0);
+    for (int i = 0; i < T && cm; i++) cm = (rows[i] == i % 8) && (cs[i] == cs[i - i % 8]);
+    if (cm) {
+      family = kCm;
+      for (int i = 0; i < T; i += 8) cols.push_back(cs[i]);
+      return true;
+    }
+    bool pm = (T == 8 * L);
+    bool seen[8] = {false};
+    for (int g = 0; g < 8 && pm; g++) {
+      const int r = rows[g * L];
+      for (int i = 0; i < L && pm; i++) pm = (rows[g * L + i] == r) && (cs[g * L + i] == cs[i]);
+      if (pm) { pm = !seen[r]; seen[r] = true; rho[g] = r; }
+    }
+    if (pm) {
+      family = kPm;
+      cols.assign(cs, cs + L);
+      return true;
+    }
+    *why = fmt("module %d: scan table is neither column-major nor plane-major", idx);
+    return false;
+  }
+
+  // ---- expressions ----
+  std::string pred_expr(int w) const {
+    const int srcs[4] = {psrc[4 * w], psrc[4 * w + 1], psrc[4 * w + 2], psrc[4 * w + 3]};
+    const std::string base = gather_expr("x", srcs);
+    const int* vals = &pval[4 * w];
+    if (op == kAdd) {
+      uint32_t d = 0;
+      for (int q = 0; q < 4; q++) d |= (uint32_t)(vals[q] & 0xFF) << (8 * q);
+      return d == 0 ? base : fmt("add_u8x4(%s, 0x%08xu)", base.c_str(), d);
+    }
+    if (op == kShift) {
+      std::map<int, std::vector<int>> groups;
+      for (int q = 0; q < 4; q++) groups[vals[q]].push_back(q);
+      if (groups.size() == 1 && groups.begin()->first == 0) return base;
+      std::vector<std::string> terms;
+      for (auto& kv : groups) {
+        const int s = kv.first;
+        if (std::abs(s) >= 8) continue;
+        uint32_t m = 0;
+        if (s >= 0) {
+          for (int q : kv.second) m |= (uint32_t)((0xFF << s) & 0xFF) << (8 * q);
+          terms.push_back(s ? fmt("((p << %d) & 0x%08xu)", s, m) : fmt("(p & 0x%08xu)", m));
+        } else {
+          for (int q : kv.second) m |= (uint32_t)(0xFF >> -s) << (8 * q);
+          terms.push_back(fmt("((p >> %d) & 0x%08xu)", -s, m));
+        }
+      }
+      if (terms.empty()) return "0u";
+      return fmt("shiftmix(%s, [](uint32_t p) { return %s; })", base.c_str(), join(terms, " | ").c_str());
+    }
+    return base;
+  }
+
+  std::string root_byte() const {
+    const int rw = root / 4, rb = root % 4;
+    return rb == 0 ? fmt("(x[%d] & 0xffu)", rw) : fmt("((x[%d] >> %d) & 0xffu)", rw, 8 * rb);
+  }
+
+  static bool plain_word(const std::string& e, int* index) {
+    if (e.size() < 4 || e.compare(0, 2, "x[") != 0 || e.back() != ']') return false;
+    for (size_t i = 2; i + 1 < e.size(); i++)
+      if (e[i] < '0' || e[i] > '9') return false;
+    *index = atoi(e.c_str() + 2);
+    return true;
+  }
+
+  // statement defining `const uint32_t <name>` = residue word w (before the XOR stage)
+  std::string residue_stmts(int w, const std::string& name, bool shared_low = false) const {
+    const int srcs[4] = {xsrc[4 * w], xsrc[4 * w + 1], xsrc[4 * w + 2], xsrc[4 * w + 3]};
+    const std::string xe = gather_expr("x", srcs), pe = pred_expr(w);
+    std::string e;
+    int a = 0, b = 0;
+    if (shared_low && plain_word(xe, &a) && plain_word(pe, &b))
+      e = fmt("sub_u8x4_shared(x[%d], x[%d], al[%d], al[%d])", a, b, a, b);
+    else
+      e = fmt("sub_u8x4(%s, %s)", xe.c_str(), pe.c_str());
+    if (w == 0) e = fmt("((%s & 0xffffff00u) | %s)", e.c_str(), root_byte().c_str());
+    return fmt("const uint32_t %s = %s;", name.c_str(), e.c_str());
+  }
+
+  // line word ^ predicted word for residue word w; a zero byte <=> that residue byte is zero
+  std::string eq_expr(int w) const {
+    const int srcs[4] = {xsrc[4 * w], xsrc[4 * w + 1], xsrc[4 * w + 2], xsrc[4 * w + 3]};
+    std::string e = fmt("(%s ^ %s)", gather_expr("x", srcs).c_str(), pred_expr(w).c_str());
+    if (w == 0) e = fmt("((%s & 0xffffff00u) | %s)", e.c_str(), root_byte().c_str());  // ResidueModule.cpp:26-27
+    return e;
+  }
+
+  std::string g_from_r(int w, const std::string& r) const {
+    if (cxor) return fmt("xc(%s, 0x%08xu)", r.c_str(), w == 0 ? 0x7f7f7f00u : 0x7f7f7f7fu);
+    return fmt("xf(%s, 0x%08xu)", r.c_str(), w == 0 ? 0x01010100u : 0x01010101u);
+  }
+};
+
+typedef std::vector<std::string> Lines;
+
+// full_<m>: all 32 residue words -> residue sums, canonical row layout c[32].
+// lut_xor != 0 (column-major modules only): the row-cost table is indexed with the residue bytes BEFORE the XOR stage --
+// the stage is a per-byte bijection (Gray code / conditional complement), so it is folded into the table and disappears
+// from the kernel; only the root byte, which the XOR stage skips (XORModule.cpp:12), is run through the inverse map so
+// that the table maps it back to itself.
+void emit_full(const Module& m, Lines& out, int lut_xor) {
+  out.push_back(fmt("__device__ __forceinline__ void full_%d(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq) {", m.idx));
+  out.push_back("  uint32_t g[32];");
+  out.push_back("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one");
+  out.push_back("  uint32_t al[32];");
+  out.push_back("#pragma unroll");
+  out.push_back("  for (int i = 0; i < 32; i++) al[i] = x[i] & 0x7f7f7f7fu;  // only the words a plain-copy predictor uses survive");
+  for (int w = 0; w < W; w++) {
+    out.push_back("  { " + m.residue_stmts(w, "r", true));
+    if (w == 0) {
+      // MAE/MSE run over all line positions (ResidueModule.cpp:43-73): the residue line holds the root byte itself at
+      // position 0, the statistics hold line[root] - predicted[root] instead
+      const int rw = m.root / 4, rb = m.root % 4, pw = m.root_pred / 4, pb = m.root_pred % 4;
+      if (m.root_pred == m.root)
+        out.push_back("    const uint32_t rs = r & 0xffffff00u;");
+      else
+        out.push_back(fmt("    const uint32_t rs = (r & 0xffffff00u) | (((x[%d] >> %d) - (x[%d] >> %d)) & 0xffu);", rw, 8 * rb, pw, 8 * pb));
+      out.push_back("    sa0 = mpcdev::sum_u8x4_acc(rs, sa0); sq0 = __dp4a(rs, rs, sq0);");
+    } else {
+      out.push_back(fmt("    sa%d = mpcdev::sum_u8x4_acc(r, sa%d); sq%d = __dp4a(r, r, sq%d);", w % 4, w % 4, w % 4, w % 4));
+    }
+    if (lut_xor && m.family == Module::kCm) {
+      if (w == 0)
+        out.push_back(fmt("    g[0] = (r & 0xffffff00u) | %s(r & 0xffu); }", lut_xor == 1 ? "inv_gray8" : "inv_first8"));
+      else
+        out.push_back(fmt("    g[%d] = r; }", w));
+    } else {
+      out.push_back(fmt("    g[%d] = %s; }", w, m.g_from_r(w, "r").c_str()));
+    }
+  }
+  out.push_back("  sa = (sa0 + sa1) + (sa2 + sa3); sq = (sq0 + sq1) + (sq2 + sq3);");
+  if (m.family == Module::kCm) {
+    std::vector<int> cols = m.cols;
+    cols.resize(L, -1);
+    for (int j = 0; j < W; j++) {
+      const int srcs[4] = {cols[4 * j + 1], cols[4 * j], cols[4 * j + 3], cols[4 * j + 2]};
+      out.push_back(fmt("  c[%d] = %s;", j, gather_expr("g", srcs).c_str()));
+    }
+  } else {
+    for (int h = 0; h < 2; h++)
+      for (int k = 0; k < 16; k++) {
+        int srcs[4];
+        for (int q = 0; q < 4; q++) srcs[q] = m.cols[16 * (4 * h + q) + k];
+        out.push_back(fmt("  c[%d] = %s;", 16 * h + k, gather_expr("g", srcs).c_str()));
+      }
+  }
+  out.push_back("}");
+}
+
+// Leading zero rows of a column-major module.  A scan row is two bytes of the XOR-ed residue line, and such a byte is
+// zero exactly when the line byte equals its prediction (both XOR variants map 0 -> 0 only), so the score needs no
+// subtraction: e<w> = line word ^ predicted word, tested under the byte masks of the row.
+void emit_score_cm(const Module& m, Lines& out) {
+  out.push_back(fmt("__device__ __forceinline__ uint32_t score_%d(const uint32_t (&x)[32]) {", m.idx));
+  std::set<int> have;
+  std::vector<int> cols = m.cols;
+  cols.resize(L, -1);
+  std::vector<std::map<int, uint32_t>> tests(64);
+  for (int k = 0; k < 64; k++)
+    for (int cidx : {cols[2 * k], cols[2 * k + 1]})
+      if (cidx >= 0) tests[k][cidx / 4] |= 0xFFu << (8 * (cidx % 4));
+  for (int k = 0; k < 64; k += 2) {
+    std::vector<int> group;
+    for (int kk : {k, k + 1})
+      if (kk < 64 && !tests[kk].empty()) group.push_back(kk);
+    for (int kk : group)
+      for (auto& wm : tests[kk])
+        if (!have.count(wm.first)) {
+          out.push_back(fmt("  const uint32_t e%d = %s;", wm.first, m.eq_expr(wm.first).c_str()));
+          have.insert(wm.first);
+        }
+    std::vector<std::pair<int, std::string>> exprs;
+    for (int kk : group) {
+      std::vector<std::pair<uint32_t, std::vector<std::string>>> terms;  // grouped by mask, first-appearance order
+      for (auto& wm : tests[kk]) {
+        auto it = std::find_if(terms.begin(), terms.end(), [&](auto& t) { return t.first == wm.second; });
+        if (it == terms.end()) { terms.push_back({wm.second, {}}); it = terms.end() - 1; }
+        it->second.push_back(fmt("e%d", wm.first));
+      }
+      std::vector<std::string> parts;
+      for (auto& t : terms)
+        parts.push_back(t.first != 0xFFFFFFFFu ? fmt("((%s) & 0x%08xu)", join(t.second, " | ").c_str(), t.first)
+                                                : fmt("(%s)", join(t.second, " | ").c_str()));
+      exprs.push_back({kk, join(parts, " | ")});
+    }
+    if (exprs.size() == 2)
+      out.push_back(fmt("  { const uint32_t t0 = %s, t1 = %s; if ((t0 | t1) != 0u) return t0 ? %du : %du; }", exprs[0].second.c_str(),
+                        exprs[1].second.c_str(), exprs[0].first, exprs[1].first));
+    else if (exprs.size() == 1)
+      out.push_back(fmt("  if ((%s) != 0u) return %du;", exprs[0].second.c_str(), exprs[0].first));
+  }
+  out.push_back("  return 64u;");
+  out.push_back("}");
+}
+
+// 8-bit value whose bit 7-p is bit 7-rho[p] of v (planes reordered into scan order)
+std::string plane_order_expr(const std::string& v, const Module& m) {
+  if (m.rho_identity()) return fmt("(%s & 0xffu)", v.c_str());
+  std::vector<std::string> terms;
+  for (int p = 0; p < 8; p++) {
+    const int src = 7 - m.rho[p], dst = 7 - p;
+    if (src >= dst) terms.push_back(fmt("(((%s) >> %d) & 0x%02xu)", v.c_str(), src - dst, 1 << dst));
+    else terms.push_back(fmt("(((%s) << %d) & 0x%02xu)", v.c_str(), dst - src, 1 << dst));
+  }
+  return "(" + join(terms, " | ") + ")";
+}
+
+void emit_score_pm(const Module& m, Lines& out) {
+  out.push_back(fmt("__device__ __forceinline__ uint32_t score_%d(const uint32_t (&x)[32]) {", m.idx));
+  out.push_back("  uint32_t g[32];");
+  const bool early = (m.rho[0] == 0);  // plane 0 (bit 7) is untouched by the XOR stage: test it on the residues alone
+  std::vector<std::map<int, uint32_t>> chunks(8);
+  for (int j = 0; j < 8; j++)
+    for (int i = 0; i < 16; i++) {
+      const int cidx = m.cols[16 * j + i];
+      chunks[j][cidx / 4] |= 0xFFu << (8 * (cidx % 4));
+    }
+  auto chunk_or = [&](int j, const char* arr) {
+    std::vector<std::string> terms;
+    for (auto& wm : chunks[j])
+      terms.push_back(wm.second != 0xFFFFFFFFu ? fmt("(%s[%d] & 0x%08xu)", arr, wm.first, wm.second) : fmt("%s[%d]", arr, wm.first));
+    return join(terms, " | ");
+  };
+  for (int w = 0; w < W; w++) out.push_back("  { " + m.residue_stmts(w, "r") + fmt(" g[%d] = r; }", w));
+  if (early) {
+    out.push_back("  {");
+    out.push_back("    uint32_t msb = 0;");
+    out.push_back("#pragma unroll");
+    out.push_back("    for (int i = 0; i < 32; i++) msb |= g[i];");
+    out.push_back("    if (msb & 0x80808080u) {  // some row of the first plane group is non-zero: z < 8");
+    for (int j = 0; j < 8; j++) out.push_back(fmt("      if ((%s) & 0x80808080u) return %du;", chunk_or(j, "g").c_str(), j));
+    out.push_back("    }");
+    out.push_back("  }");
+  }
+  if (!m.rho_identity()) {
+    for (int w = 0; w < W; w++) out.push_back(fmt("  g[%d] = %s;", w, m.g_from_r(w, fmt("g[%d]", w)).c_str()));
+  } else {
+    out.push_back("  // planes are scanned MSB first: while every higher plane is zero, plane b of the XOR-ed residue equals");
+    out.push_back("  // plane b of the residue itself (XORModule.cpp:9-20), so the leading-zero count needs no XOR stage");
+  }
+  out.push_back("  uint32_t f[8];");
+  for (int j = 0; j < 8; j++)
+    out.push_back(fmt("  { uint32_t o = %s; o |= o >> 16; o |= o >> 8; f[%d] = %s; }", chunk_or(j, "g").c_str(), j, plane_order_expr("o", m).c_str()));
+  out.push_back("  return pm_leading_zero_rows(f);");
+  out.push_back("}");
+}
+
+// after transpose8x8 byte c holds plane 7-c; output byte p must hold plane rho[p]
+std::pair<unsigned, unsigned> pm_selectors(const Module& m) {
+  unsigned s0 = 0, s1 = 0;
+  for (int p = 0; p < 4; p++) {
+    s0 |= (unsigned)(7 - m.rho[p]) << (4 * p);
+    s1 |= (unsigned)(7 - m.rho[4 + p]) << (4 * p);
+  }
+  return {s0, s1};
+}
+
+template <class T>
+std::string int_array(const T* vals, int count, int width) {
+  std::string s = "{";
+  for (int i = 0; i < width; i++) {
+    if (i) s += ",";
+    s += std::to_string(i < count ? (int)vals[i] : 0);
+  }
+  return s + "}";
+}
+
+std::string pod_initializer(const mpc_config_pod& c) {
+  std::vector<std::string> mods;
+  for (int i = 0; i < MPC_MAX_MODULES; i++) {
+    if (i >= c.num_modules) { mods.push_back("{}"); continue; }
+    const mpc_module_pod& m = c.modules[i];
+    if (m.kind == MPC_MOD_ALLZERO) mods.push_back("{MPC_MOD_ALLZERO}");
+    else if (m.kind == MPC_MOD_ALLWORDSAME) mods.push_back("{MPC_MOD_ALLWORDSAME}");
+    else
+      mods.push_back(fmt("{MPC_MOD_PREDCOMP, %d, %d, %d, %d, ", m.predictor, m.root, m.consecutive_xor, m.table_size) +
+                     int_array(m.base, L, L) + ", " + int_array(m.diff, L, L) + ", " + int_array(m.shift, L, L) + ", " +
+                     int_array(m.scan_row, m.table_size, 8 * L) + ", " + int_array(m.scan_col, m.table_size, 8 * L) + "}");
+  }
+  return fmt("{%d, %d, %d, %d, ", c.line_size, c.num_modules, c.has_wordsame, c.first_predcomp) +
+         int_array(c.enc_bits, c.num_modules + 1, MPC_MAX_MODULES + 1) + ", {" + join(mods, ",\n   ") + "}}";
+}
+
+bool build_modules(const mpc_config_pod& cfg, std::vector<Module>* mods, std::string* why) {
+  if (cfg.line_size != L) { *why = "lineSize != 128"; return false; }
+  if (cfg.num_modules < 1 || cfg.num_modules > MPC_MAX_MODULES) { *why = "num_modules out of range"; return false; }
+  for (int i = cfg.first_predcomp; i < cfg.num_modules; i++) {
+    Module m;
+    if (!m.init(i, cfg.modules[i], why)) return false;
+    mods->push_back(m);
+  }
+  return true;
+}
+
+}  // namespace
+
+bool spec_eligible(const mpc_config_pod& cfg, std::string* why) {
+  std::vector<Module> mods;
+  std::string w;
+  const bool ok = build_modules(cfg, &mods, &w);
+  if (why) *why = w;
+  return ok;
+}
+
+SpecTraits spec_traits(const mpc_config_pod& cfg) {
+  SpecTraits t;
+  std::vector<Module> mods;
+  std::string why;
+  if (!build_modules(cfg, &mods, &why)) return t;
+  bool has_pm = false, has_cm = false, all_c = true, any_c = false;
+  for (auto& m : mods) {
+    if (m.family == Module::kPm) has_pm = true;
+    else { has_cm = true; all_c = all_c && m.cxor; any_c = any_c || m.cxor; }
+  }
+  const char* e;
+  t.eligible = true;
+  t.use_lut = has_cm && !((e = getenv("MPC_SPEC_LUT")) && e[0] == '0');
+  t.lut_xor = 0;
+  if (t.use_lut && !((e = getenv("MPC_SPEC_LUTXOR")) && e[0] == '0')) t.lut_xor = all_c ? 1 : (!any_c ? 2 : 0);
+  t.warps = (t.use_lut && !has_pm) ? 16 : 8;
+  t.min_ctas = has_pm ? 1 : 2;
+  if ((e = getenv("MPC_SPEC_MIN_CTAS")) && atoi(e) > 0) t.min_ctas = atoi(e);
+  if (t.warps == 16) t.min_ctas = 1;
+  e = getenv("MPC_SPEC_SKIP");
+  t.skip_zero_groups = e ? (e[0] != '0') : !t.use_lut;
+  t.smem_bytes = (size_t)t.warps * 2 * 4096 + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
+                 (t.use_lut ? 65536 : 0);
+  return t;
+}
+
+std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& name, bool jit, std::string* why) {
+  std::vector<Module> mods;
+  std::string w;
+  if (!build_modules(cfg, &mods, &w)) {
+    if (why) *why = w;
+    return std::string();
+  }
+  const SpecTraits t = spec_traits(cfg);
+  const int n = cfg.num_modules, first = cfg.first_predcomp;
+  Lines out;
+  if (jit) {
+    out.push_back("// Generated at run time by libmpc_b200 (mpc_specgen.cpp) for a config without a compiled-in specialisation.");
+  } else {
+    out.push_back(fmt("// AUTO-GENERATED by tools/specgen (csrc/mpc_specgen.cpp) from configs/%s.json -- do not edit.", name.c_str()));
+    out.push_back("// Straight-line schedule of the MPC per-block path for this config over the primitives of mpc_spec.cuh.");
+  }
+  out.push_back(jit ? "#include \"mpc_spec.cuh\"" : "#include \"../mpc_spec.cuh\"");
+  if (!jit) out.push_back("#include \"../mpc_spec.h\"");
+  out.push_back("");
+  out.push_back("namespace mpc {");
+  out.push_back(fmt("namespace spec_%s {", name.c_str()));
+  out.push_back("using namespace mpc::spec;");
+  out.push_back("template <class F> __device__ __forceinline__ uint32_t shiftmix(uint32_t p, F f) { return f(p); }");
+  out.push_back("");
+  static const char* kPredNames[] = {"OneBasePredictor", "ConsecutiveBasePredictor", "DiffBasePredictor", "WeightBasePredictor"};
+  for (auto& m : mods) {
+    out.push_back(fmt("// ---- module %d: %s, root %d, %s XOR, %s-major scan ----", m.idx, kPredNames[m.predictor], m.root,
+                      m.cxor ? "consecutive" : "first-plane", m.family == Module::kCm ? "column" : "plane"));
+    if (m.family == Module::kCm) emit_score_cm(m, out); else emit_score_pm(m, out);
+    emit_full(m, out, t.lut_xor);
+    out.push_back("");
+  }
+  out.push_back("struct Cfg {");
+  out.push_back(fmt("  static constexpr int kNumModules = %d;", n));
+  out.push_back(fmt("  static constexpr int kFirst = %d;", first));
+  out.push_back(fmt("  static constexpr bool kHasWordSame = %s;", cfg.has_wordsame ? "true" : "false"));
+  // register budget: plane-major modules keep the line, its residues and the transposed rows live at once;
+  // column-major only: 16 warps in ONE CTA per SM (<= 128 registers) so that the 64 KiB row-cost table, the 128 KiB of
+  // tile stages and the histogram fit the 227 KiB of shared memory
+  out.push_back(fmt("  static constexpr int kWarps = %d;", t.warps));
+  out.push_back(fmt("  static constexpr bool kUseLut = %s;  // shared-memory row-cost table (column-major modules)", t.use_lut ? "true" : "false"));
+  out.push_back(fmt("  static constexpr bool kSkipZeroGroups = %s;  // branch around groups of eight zero rows in the encoder", t.skip_zero_groups ? "true" : "false"));
+  out.push_back(fmt("  static constexpr int kLutXor = %d;  // 0: table indexed by scan rows; 1 / 2: XOR stage (consecutive / first-plane) folded into the table",
+                    t.use_lut ? t.lut_xor : 0));
+  out.push_back(fmt("  static constexpr int kMinCtasPerSm = %d;  // __launch_bounds__: register budget 65536 / (threads * CTAs)", t.min_ctas));
+  out.push_back("  __device__ static __forceinline__ uint32_t enc(int k) {  // encoding bits of cluster k-1, VPC.cpp:102-117");
+  out.push_back("    switch (k) {");
+  for (int k = 0; k <= n; k++) out.push_back(fmt("      case %d: return %du;", k, cfg.enc_bits[k]));
+  out.push_back("    }");
+  out.push_back("    return 0u;");
+  out.push_back("  }");
+  out.push_back("  // VPC.cpp:372-395: most leading zero rows wins, ties go to the later module");
+  out.push_back("  __device__ static __forceinline__ void select(const uint32_t (&x)[32], int& best, uint32_t& bestz, unsigned lanes) {");
+  out.push_back("    uint32_t z;");
+  for (size_t i = 0; i + 1 < mods.size(); i++)
+    out.push_back(fmt("    z = score_%d(x); if (bestz <= z) { best = %d; bestz = z; }", mods[i].idx, mods[i].idx));
+  if (!mods.empty()) {
+    const int li = mods.back().idx;
+    out.push_back("    // the last module wins every tie, so while no earlier module has a zero row it wins unscored");
+    out.push_back(fmt("    if (bestz == 0u) { best = %d; } else { z = score_%d(x); if (bestz <= z) { best = %d; bestz = z; } }", li, li, li));
+    out.push_back("    __syncwarp(lanes);  // reconverge before the encoder: both sides of the branch share it");
+  } else {
+    out.push_back("    (void)z; (void)x; (void)best; (void)bestz; (void)lanes;");
+  }
+  out.push_back("  }");
+  out.push_back("  // residue sums (VPC.cpp:417-443) + common encoder (FPCModule.cpp:19-85) of the chosen module");
+  out.push_back("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq, unsigned lanes, const uint8_t* lut) {");
+  out.push_back("    uint32_t c[32];");
+  // encoder families in use: column-major, or plane-major with a given pair of plane selectors
+  std::vector<std::pair<int, std::pair<unsigned, unsigned>>> fams;
+  auto fam_of = [&](const Module& m) {
+    return std::make_pair(m.family == Module::kCm ? 0 : 1, m.family == Module::kPm ? pm_selectors(m) : std::make_pair(0u, 0u));
+  };
+  for (auto& m : mods)
+    if (std::find(fams.begin(), fams.end(), fam_of(m)) == fams.end()) fams.push_back(fam_of(m));
+  std::sort(fams.begin(), fams.end());
+  out.push_back("    int fam = 0;");
+  out.push_back("    switch (best) {");
+  for (auto& m : mods) {
+    const int fid = (int)(std::find(fams.begin(), fams.end(), fam_of(m)) - fams.begin());
+    out.push_back(fmt("      case %d: full_%d(x, c, sa, sq); fam = %d; break;", m.idx, m.idx, fid));
+  }
+  out.push_back("      default: break;");
+  out.push_back("    }");
+  out.push_back("    __syncwarp(lanes);  // the row classifier below is shared by all modules: run it once per warp");
+  auto call = [&](const std::pair<int, std::pair<unsigned, unsigned>>& f) {
+    return f.first == 0 ? std::string("encode_cm<kUseLut, kSkipZeroGroups>(c, lut)")
+                        : fmt("encode_pm<0x%04xu, 0x%04xu>(c)", f.second.first, f.second.second);
+  };
+  if (fams.size() == 1) {
+    out.push_back("    (void)fam;");
+    out.push_back("    return " + call(fams[0]) + ";");
+  } else {
+    for (size_t i = 0; i < fams.size(); i++) out.push_back(fmt("    if (fam == %d) return %s;", (int)i, call(fams[i]).c_str()));
+    if (fams.empty()) out.push_back("    (void)fam; (void)c; (void)x; (void)sa; (void)sq; (void)lut;");
+    out.push_back("    return 0u;");
+  }
+  out.push_back("  }");
+  out.push_back("};");
+  out.push_back("");
+  if (jit) {
+    out.push_back(fmt("}  // namespace spec_%s", name.c_str()));
+    out.push_back("}  // namespace mpc");
+    out.push_back(fmt("extern \"C\" __global__ void __launch_bounds__(mpc::spec_%s::Cfg::kWarps * 32, mpc::spec_%s::Cfg::kMinCtasPerSm)", name.c_str(), name.c_str()));
+    out.push_back("mpc_jit_kernel(const uint4* __restrict__ lines, unsigned long long n_blocks, unsigned short* __restrict__ packed,");
+    out.push_back("               unsigned long long* __restrict__ stats, const uint4* __restrict__ row_lut) {");
+    out.push_back(fmt("  mpc::spec::spec_kernel_body<mpc::spec_%s::Cfg>(lines, n_blocks, packed, stats, row_lut);", name.c_str()));
+    out.push_back("}");
+  } else {
+    out.push_back("static const mpc_config_pod kPod =");
+    out.push_back("  " + pod_initializer(cfg) + ";");
+    out.push_back("");
+    out.push_back("static bool matches(const mpc_config_pod& cfg) { return spec_pod_equal(cfg, kPod); }");
+    out.push_back("static cudaError_t launch(const mpc_config_pod&, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed,");
+    out.push_back("                          uint64_t* d_stats, const uint8_t* d_row_lut, int sm_count, cudaStream_t stream) {");
+    out.push_back("  return launch_spec<Cfg>(d_lines, n_blocks, d_packed, d_stats, d_row_lut, sm_count, stream);");
+    out.push_back("}");
+    out.push_back(fmt("}  // namespace spec_%s", name.c_str()));
+    out.push_back(fmt("extern const SpecKernel kSpec_%s = {\"%s\", spec_%s::matches, spec_%s::launch, spec_%s::Cfg::kLutXor};", name.c_str(),
+                      name.c_str(), name.c_str(), name.c_str(), name.c_str()));
+    out.push_back("}  // namespace mpc");
+  }
+  std::string text;
+  for (auto& l : out) { text += l; text += "\n"; }
+  return text;
+}
+
+}  // namespace mpc

@@ -1,0 +1,27 @@
+// Config compiler interface (mpc_specgen.cpp): config -> source of a specialised kernel schedule.
+#pragma once
+#include <cstddef>
+#include <string>
+
+#include "mpc_capi.h"
+
+namespace mpc {
+
+struct SpecTraits {
+  bool eligible = false;
+  bool use_lut = false;          // column-major modules: 64 KiB shared-memory row-cost table
+  int lut_xor = 0;               // 0 plain table, 1 / 2: consecutive / first-plane XOR stage folded into the table
+  int warps = 8;                 // warps per CTA
+  int min_ctas = 2;              // __launch_bounds__ second argument
+  bool skip_zero_groups = true;  // encoder branches around groups of eight zero rows
+  size_t smem_bytes = 0;         // dynamic shared memory of one CTA
+};
+
+// true when a specialised kernel can be generated for cfg (lineSize 128, every scan column- or plane-major)
+bool spec_eligible(const mpc_config_pod& cfg, std::string* why);
+SpecTraits spec_traits(const mpc_config_pod& cfg);
+// jit = false: translation unit for the ahead-of-time build (registers itself as kSpec_<name>);
+// jit = true: NVRTC translation unit exposing `extern "C" __global__ mpc_jit_kernel`.  Empty string + *why when not eligible.
+std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& name, bool jit, std::string* why);
+
+}  // namespace mpc
