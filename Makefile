@@ -14,7 +14,7 @@ SPEC_CFGS := P6 F4 Z1 E5
 SPEC_SRCS := $(foreach c,$(SPEC_CFGS),$(CSRC)/spec/spec_$(c).cu)
 CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_variants.cu $(CSRC)/mpc_sc2.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu $(SPEC_SRCS)
 CU_OBJS  := $(CU_SRCS:.cu=.o)
-CC_OBJS  := $(CSRC)/mpc_config.o $(CSRC)/mpc_specgen.o
+CC_OBJS  := $(CSRC)/mpc_config.o $(CSRC)/mpc_specgen.o $(CSRC)/mpc_jit.o
 
 all: $(LIB) compressor oracle
 
@@ -35,11 +35,18 @@ $(CSRC)/spec/%.o: $(CSRC)/spec/%.cu $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include
 $(CSRC)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+# headers the run-time (NVRTC) build of the specialised kernel compiles against, embedded as raw string literals
+EMBED_HDRS := mpc_spec.cuh mpc_device.cuh mpc_layout.h
+$(CSRC)/mpc_embedded_headers.inc: $(foreach h,$(EMBED_HDRS),$(CSRC)/$(h))
+	@rm -f $@; for h in $(EMBED_HDRS); do \
+	  printf 'static const char kHdr_%s[] = R"MPCHDR(' "$$(echo $$h | tr . _)" >> $@; cat $(CSRC)/$$h >> $@; printf ')MPCHDR";\n' >> $@; done
+$(CSRC)/mpc_jit.o: $(CSRC)/mpc_embedded_headers.inc
+
 $(CSRC)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h include/*.h)
-	$(CXX) $(CXXFLAGS) -c $< -o $@
+	$(CXX) $(CXXFLAGS) -I/usr/local/cuda/include -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(CC_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -Xlinker --no-undefined
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -lnvrtc -Xlinker --no-undefined -Xlinker -rpath=/usr/local/cuda/lib64
 
 HOST_SRCS := $(wildcard $(HOST)/*.cpp $(HOST)/compressor/*.cpp $(HOST)/loader/*.cpp)
 compressor: bin/compressor

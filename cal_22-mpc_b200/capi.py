@@ -60,7 +60,7 @@ SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config
            "mpc_submit_device", "mpc_submit_host", "mpc_sync", "mpc_stats_device_ptr", "mpc_finish",
            "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version",
            "mpc_variant_run_device", "mpc_variant_run_host", "mpc_variant_error", "mpc_sc2_run_device", "mpc_sc2_run_host",
-           "mpc_sc2_error", "mpc_cpack_run_host"]
+           "mpc_sc2_error", "mpc_cpack_run_host", "mpc_jit_compile_check"]
 
 
 def lib():
@@ -83,6 +83,7 @@ def lib():
     l.mpc_set_kernel.argtypes = [vp, C.c_int]
     l.mpc_kernel_name.argtypes = [vp]
     l.mpc_set_stream.argtypes = [vp, vp]
+    l.mpc_jit_compile_check.argtypes = [C.POINTER(ConfigPod), C.c_char_p, sz, C.POINTER(sz)]
     l.mpc_kernel_name.restype = C.c_char_p
     l.mpc_submit_device.argtypes = [vp, vp, u64, vp]
     l.mpc_submit_host.argtypes = [vp, vp, u64, vp]
@@ -116,6 +117,15 @@ def load_config(path=None, text=None):
     if rc != 0:
         raise MpcError(f"config rejected ({rc}): {err.value.decode(errors='replace')}")
     return pod
+
+
+def jit_compile_check(config):
+    """Config compiler + NVRTC on the CPU: -> (return code, cubin bytes, log)."""
+    pod = config if isinstance(config, ConfigPod) else load_config(path=config)
+    log = C.create_string_buffer(1 << 16)
+    n = C.c_size_t()
+    rc = lib().mpc_jit_compile_check(C.byref(pod), log, len(log), C.byref(n))
+    return rc, n.value, log.value.decode(errors="replace")
 
 
 class Stats:

@@ -12,6 +12,7 @@
 
 #include "mpc_capi.h"
 #include "mpc_internal.h"
+#include "mpc_jit.h"
 #include "mpc_spec.h"
 
 namespace {
@@ -41,6 +42,7 @@ struct mpc_ctx {
   mpc::GenericModule* d_gmods = nullptr;
   const mpc::SpecKernel* spec = nullptr;  // specialised kernel matching cfg, if any
   uint8_t* d_row_lut = nullptr;           // row-cost table used by the specialised kernels
+  mpc::JitKernel* jit = nullptr;          // specialised kernel built at run time (NVRTC) when none is compiled in
   int kernel_choice = 0;
   uint64_t* d_stats = nullptr;
   cudaStream_t own_stream = nullptr;      // created by mpc_create
@@ -54,6 +56,7 @@ struct mpc_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_host_events;
   std::string error;
   std::string kernel_name;
+  std::string jit_note;  // why no specialised kernel exists for this context, if that is the case
 };
 
 namespace {
@@ -77,17 +80,20 @@ int fail(mpc_ctx* ctx, int code, const char* fmt, ...) {
 
 bool use_spec(const mpc_ctx* ctx) {
   if (ctx->kernel_choice == 1) return false;
-  return ctx->spec != nullptr;
+  return ctx->spec != nullptr || ctx->jit != nullptr;
 }
 
 void refresh_kernel_name(mpc_ctx* ctx) {
-  ctx->kernel_name = use_spec(ctx) ? (std::string("spec_thread:") + ctx->spec->name) : std::string("generic_warp");
+  if (!use_spec(ctx)) ctx->kernel_name = "generic_warp";
+  else ctx->kernel_name = std::string("spec_thread:") + (ctx->spec ? ctx->spec->name : "jit");
 }
 
 int launch(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n, uint16_t* d_packed, cudaStream_t s) {
   cudaError_t e;
-  if (use_spec(ctx))
+  if (use_spec(ctx) && ctx->spec)
     e = ctx->spec->launch(ctx->cfg, d_lines, n, d_packed, ctx->d_stats, ctx->d_row_lut, ctx->sm_count, s);
+  else if (use_spec(ctx))
+    e = mpc::jit_launch(ctx->jit, d_lines, n, d_packed, ctx->d_stats, ctx->d_row_lut, ctx->sm_count, s);
   else
     e = mpc::launch_generic(ctx->gparams, ctx->d_gmods, d_lines, n, d_packed, ctx->d_stats, ctx->sm_count, s);
   if (e != cudaSuccess) return fail(ctx, MPC_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -185,9 +191,22 @@ int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out) {
   MPC_CREATE_CUDA(cudaMalloc(&ctx->d_gmods, gbytes));
   MPC_CREATE_CUDA(cudaMemcpyAsync(ctx->d_gmods, gm.data(), gbytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->spec = mpc::find_spec_kernel(ctx->cfg);
+  if (!ctx->spec) {
+    // no compiled-in specialisation: build one now with NVRTC when the config is eligible (MPC_JIT=0 disables);
+    // a config that is not eligible, or a failed build, leaves the generic kernel in charge and says why
+    const char* env = getenv("MPC_JIT");
+    std::string why;
+    if (env && env[0] == '0') ctx->jit_note = "run-time specialisation disabled (MPC_JIT=0)";
+    else if (!mpc::spec_eligible(ctx->cfg, &why)) ctx->jit_note = "not eligible for the specialised kernel: " + why;
+    else {
+      std::string log;
+      ctx->jit = mpc::jit_create(ctx->cfg, &log);
+      if (!ctx->jit) ctx->jit_note = "run-time specialisation failed: " + log;
+    }
+  }
   {
     std::vector<uint8_t> lut(65536);
-    mpc::build_row_cost_lut(lut.data(), ctx->spec ? ctx->spec->lut_xor : 0);
+    mpc::build_row_cost_lut(lut.data(), ctx->spec ? ctx->spec->lut_xor : (ctx->jit ? mpc::jit_lut_xor(ctx->jit) : 0));
     MPC_CREATE_CUDA(cudaMalloc(&ctx->d_row_lut, lut.size()));
     MPC_CREATE_CUDA(cudaMemcpy(ctx->d_row_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
   }
@@ -214,6 +233,7 @@ void mpc_destroy(mpc_ctx* ctx) {
   }
   if (ctx->d_gmods) cudaFree(ctx->d_gmods);
   if (ctx->d_row_lut) cudaFree(ctx->d_row_lut);
+  if (ctx->jit) mpc::jit_destroy(ctx->jit);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -225,14 +245,25 @@ void mpc_destroy(mpc_ctx* ctx) {
 int mpc_set_kernel(mpc_ctx* ctx, int which) {
   if (!ctx) return MPC_E_ARG;
   if (which < 0 || which > 2) return fail(ctx, MPC_E_ARG, "mpc_set_kernel: which = %d", which);
-  if (which == 2 && !ctx->spec)
-    return fail(ctx, MPC_E_STATE, "no specialised kernel is built into this library for the given config");
+  if (which == 2 && !ctx->spec && !ctx->jit)
+    return fail(ctx, MPC_E_STATE, "no specialised kernel for the given config (%s)", ctx->jit_note.c_str());
   ctx->kernel_choice = which;
   refresh_kernel_name(ctx);
   return MPC_OK;
 }
 
 const char* mpc_kernel_name(const mpc_ctx* ctx) { return ctx ? ctx->kernel_name.c_str() : ""; }
+
+int mpc_jit_compile_check(const mpc_config_pod* cfg, char* log, size_t log_len, size_t* cubin_bytes) {
+  if (!cfg) return MPC_E_ARG;
+  std::vector<char> cubin;
+  std::string l;
+  mpc::SpecTraits t;
+  const int rc = mpc::jit_compile(*cfg, &cubin, &t, &l);
+  if (log && log_len) snprintf(log, log_len, "%s", l.c_str());
+  if (cubin_bytes) *cubin_bytes = cubin.size();
+  return rc;
+}
 
 int mpc_set_stream(mpc_ctx* ctx, void* cuda_stream) {
   if (!ctx) return MPC_E_ARG;

@@ -5,7 +5,20 @@
 // the bit tricks exhaustively on the CPU (tests/test_swar_host.py); on the device the
 // intrinsics map to PRMT / LOP3 / VIMNMX.U16x2 / VABSDIFF4 / IDP.4A.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC has no host headers: fixed-width types by hand (LP64)
+typedef unsigned char uint8_t;
+typedef signed char int8_t;
+typedef unsigned short uint16_t;
+typedef short int16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned long size_t;
+#else
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define MPC_HD __host__ __device__ __forceinline__

@@ -6,20 +6,11 @@
 #include <string>
 
 #include "mpc_capi.h"
+#include "mpc_layout.h"
 
 namespace mpc {
 
-// ---- device statistics vector (uint64 words), see MPC_STATS_WORDS ---------------------------------
-//   [0, K)            sum over stage-3 lines of sum_i |r_i|      per cluster k = selected + 1
-//   [K, 2K)           sum over stage-3 lines of sum_i r_i^2
-//   [2K, 2K + K*HB)   histogram  hist[k][size]        (K = MPC_MAX_MODULES + 1, HB = MPC_HIST_BINS)
-// Counts and compressed-size totals are derived from the histogram on the host.
-constexpr int kK = MPC_MAX_MODULES + 1;
-constexpr int kHB = MPC_HIST_BINS;
-constexpr size_t kStatsWords = MPC_STATS_WORDS;
-constexpr size_t kResAbsOff = 0;
-constexpr size_t kResSqOff = kK;
-constexpr size_t kHistOff = 2 * kK;
+static_assert(kK == MPC_MAX_MODULES + 1 && kHB == MPC_HIST_BINS && kStatsWords == MPC_STATS_WORDS, "mpc_layout.h out of sync with mpc_capi.h");
 
 // ---- generic kernel tables (one per PredComp module), built on the host from mpc_module_pod ---------
 struct GenericModule {

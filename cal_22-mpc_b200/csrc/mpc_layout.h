@@ -1,0 +1,14 @@
+// Layout of the device statistics vector (uint64 words); shared by host code, nvcc and NVRTC translation units.
+//   [0, K)            sum over stage-3 lines of sum_i |r_i|      per cluster k = selected + 1
+//   [K, 2K)           sum over stage-3 lines of sum_i r_i^2
+//   [2K, 2K + K*HB)   histogram  hist[k][size]        (K = MPC_MAX_MODULES + 1 = 17, HB = MPC_HIST_BINS = 1056)
+// Counts and compressed-size totals are derived from the histogram on the host (mpc_stats_expand).
+#pragma once
+namespace mpc {
+constexpr int kK = 16 + 1;
+constexpr int kHB = 8 * 128 + 32;
+constexpr unsigned long long kStatsWords = 2ull * kK + (unsigned long long)kK * kHB;
+constexpr unsigned long long kResAbsOff = 0;
+constexpr unsigned long long kResSqOff = kK;
+constexpr unsigned long long kHistOff = 2 * kK;
+}  // namespace mpc

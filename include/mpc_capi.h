@@ -94,10 +94,17 @@ const char* mpc_last_error(const mpc_ctx* ctx);
 const char* mpc_global_error(void);
 
 /* kernel selection: 0 = auto (specialised kernel when one exists for the config, else generic),
- * 1 = generic warp-per-block kernel, 2 = specialised thread-per-block kernel (error if none). */
+ * 1 = generic warp-per-block kernel, 2 = specialised thread-per-block kernel (error if none).
+ * A specialised kernel exists for the configs compiled into the library and, for any other config with 128-byte
+ * lines and column- or plane-major scan tables, is built at mpc_create time with NVRTC (a few seconds; MPC_JIT=0
+ * disables it, MPC_JIT_CACHE_DIR=<dir> keeps the cubins on disk). */
 int mpc_set_kernel(mpc_ctx* ctx, int which);
-/* name of the kernel the next submit will launch ("generic_warp", "spec_thread:<cfg>") */
+/* name of the kernel the next submit will launch ("generic_warp", "spec_thread:<cfg>", "spec_thread:jit") */
 const char* mpc_kernel_name(const mpc_ctx* ctx);
+
+/* Run the config compiler + NVRTC for cfg without touching a device (build check / tooling): MPC_OK and the size of
+ * the sm_100a cubin, MPC_E_CONFIG when the config is not eligible, MPC_E_STATE + compiler log on a build error. */
+int mpc_jit_compile_check(const mpc_config_pod* cfg, char* log, size_t log_len, size_t* cubin_bytes);
 
 /* Run mpc_submit_device / mpc_synth_device / statistics resets on the caller's CUDA stream (a cudaStream_t
  * passed as void*; NULL restores the context's own stream), so that the caller's events and collectives

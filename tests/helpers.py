@@ -45,9 +45,13 @@ def random_config(rng, L=128, n_pred=None, allow_root=True, table="random"):
         if mode == "cm":
             cols = rng.permutation(L)
             rows_, cols_ = np.tile(np.arange(8), L), np.repeat(cols, 8)
-        elif mode == "pm":
+        elif mode in ("pm", "pmr"):
             cols = rng.permutation(L)
-            rows_, cols_ = np.repeat(np.arange(8), L), np.tile(cols, 8)
+            planes = rng.permutation(8) if mode == "pmr" else np.arange(8)
+            rows_, cols_ = np.repeat(planes, L), np.tile(cols, 8)
+        elif mode == "cms":  # column-major over a subset of the columns (short table)
+            cols = rng.permutation(L)[: int(rng.integers(1, L))]
+            rows_, cols_ = np.tile(np.arange(8), len(cols)), np.repeat(cols, 8)
         else:
             idx = rng.permutation(nb)
             if mode == "dup":

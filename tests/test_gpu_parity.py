@@ -176,12 +176,13 @@ def test_shipped_configs_use_the_specialised_kernel(mpcb, cfg):
     assert m.kernel_name() == "spec_thread:" + cfg
 
 
-def test_unknown_config_falls_back_to_generic_and_says_so(mpcb):
+def test_ineligible_config_falls_back_to_generic_and_says_so(mpcb):
     rng = np.random.default_rng(5)
     m = mpcb.Mpc(mpcb.load_config(text=json.dumps(random_config(rng, L=64, n_pred=2))))
     assert m.kernel_name() == "generic_warp"
-    with pytest.raises(mpcb.MpcError):
+    with pytest.raises(mpcb.MpcError) as e:
         m.set_kernel(2)
+    assert "not eligible" in str(e.value)
 
 
 def test_mixed_dump_fires_every_branch(mpcb):

@@ -1,0 +1,77 @@
+"""Run-time specialisation: the config compiler (csrc/mpc_specgen.cpp) + NVRTC build a thread-per-block kernel for any
+config with 128-byte lines and column-/plane-major scan tables.  CPU: the generated sources compile for sm_100a.
+GPU: the kernels are bit-exact against the oracle."""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import SHIPPED, cfg_path, random_blocks, random_config
+from oracle.bridge import OracleMPC
+
+
+def eligible_config(seed):
+    rng = np.random.default_rng(seed)
+    mode = ["cm", "pm", "pmr", "cms", "cm", "pm"][seed % 6]
+    cfg = random_config(rng, L=128, n_pred=int(rng.integers(1, 5)), table=mode)
+    if seed % 4 == 3:  # mixed families in one config
+        other = random_config(rng, L=128, n_pred=1, table="pm" if mode.startswith("cm") else "cm")
+        first = [k for k in sorted(other["modules"], key=int) if other["modules"][k]["name"] == "PredComp"][0]
+        n = cfg["overview"]["num_modules"]
+        cfg["modules"][str(n)] = other["modules"][first]
+        cfg["overview"]["num_modules"] = n + 1
+        if "encoding_bits" in cfg["overview"]:
+            cfg["overview"]["encoding_bits"].append(3)
+    return cfg
+
+
+@pytest.mark.parametrize("cfg", SHIPPED)
+def test_shipped_configs_compile_with_nvrtc(mpcb, cfg):
+    rc, nbytes, log = mpcb.jit_compile_check(cfg_path(cfg))
+    assert rc == 0 and nbytes > 10000, log
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_eligible_configs_compile(mpcb, seed):
+    pod = mpcb.load_config(text=json.dumps(eligible_config(seed)))
+    rc, nbytes, log = mpcb.jit_compile_check(pod)
+    assert rc == 0 and nbytes > 10000, log
+
+
+def test_ineligible_configs_are_reported(mpcb):
+    rng = np.random.default_rng(1)
+    pod = mpcb.load_config(text=json.dumps(random_config(rng, L=128, n_pred=2, table="perm")))
+    rc, _, log = mpcb.jit_compile_check(pod)
+    assert rc == -2 and "neither column-major nor plane-major" in log
+    pod = mpcb.load_config(text=json.dumps(random_config(rng, L=64, n_pred=2, table="cm")))
+    rc, _, log = mpcb.jit_compile_check(pod)
+    assert rc == -2 and "lineSize" in log
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_jit_kernels_match_oracle(mpcb, seed):
+    cfg = eligible_config(100 + seed)
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(cfg)))
+    assert m.kernel_name() == "spec_thread:jit"
+    rng = np.random.default_rng(seed)
+    blocks = random_blocks(rng, 3000)
+    sizes, sels, st = m.compress(blocks)
+    r = OracleMPC(cfg).run(blocks)
+    bad = np.nonzero((sizes != r.sizes) | (sels != r.sels))[0]
+    assert bad.size == 0, (bad[:5], sizes[bad[:5]], r.sizes[bad[:5]], sels[bad[:5]], r.sels[bad[:5]])
+    assert st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count)
+    assert np.array_equal(st.res_abs, r.res_abs) and np.array_equal(st.res_sq, r.res_sq)
+    m.set_kernel(1)  # the generic kernel agrees, too
+    sizes2, sels2, _ = m.compress(blocks)
+    assert np.array_equal(sizes2, sizes) and np.array_equal(sels2, sels)
+
+
+@pytest.mark.gpu
+def test_jit_can_be_disabled(mpcb, monkeypatch):
+    monkeypatch.setenv("MPC_JIT", "0")
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(eligible_config(7))))
+    assert m.kernel_name() == "generic_warp"
+    with pytest.raises(mpcb.MpcError) as e:
+        m.set_kernel(2)
+    assert "MPC_JIT=0" in str(e.value)
