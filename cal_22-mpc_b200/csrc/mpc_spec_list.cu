@@ -1,4 +1,4 @@
-// Specialised kernels linked into the library (spec/spec_list.inc is written by tools/gen_spec.py).
+// Specialised kernels linked into the library (spec/spec_list.inc is written by tools/specgen).
 #include "mpc_spec.h"
 
 namespace mpc {
