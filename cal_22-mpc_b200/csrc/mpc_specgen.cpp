@@ -382,16 +382,23 @@ void emit_score_pm(const Module& m, Lines& out) {
       terms.push_back(wm.second != 0xFFFFFFFFu ? fmt("(%s[%d] & 0x%08xu)", arr, wm.first, wm.second) : fmt("%s[%d]", arr, wm.first));
     return join(terms, " | ");
   };
-  for (int w = 0; w < W; w++) out.push_back("  { " + m.residue_stmts(w, "r") + fmt(" g[%d] = r; }", w));
   if (early) {
-    out.push_back("  {");
-    out.push_back("    uint32_t msb = 0;");
-    out.push_back("#pragma unroll");
-    out.push_back("    for (int i = 0; i < 32; i++) msb |= g[i];");
-    out.push_back("    if (msb & 0x80808080u) {  // some row of the first plane group is non-zero: z < 8");
-    for (int j = 0; j < 8; j++) out.push_back(fmt("      if ((%s) & 0x80808080u) return %du;", chunk_or(j, "g").c_str(), j));
-    out.push_back("    }");
-    out.push_back("  }");
+    // Rows 0..7 are plane 0 of the eight column chunks, and plane 0 (bit 7) is untouched by the XOR stage: walk the
+    // chunks in scan order, computing only the residue words a chunk needs, and stop at the first set bit -- a module
+    // that loses on its first rows costs a handful of words instead of the whole line.
+    std::set<int> have;
+    for (int j = 0; j < 8; j++) {
+      for (auto& wm : chunks[j])
+        if (!have.count(wm.first)) {
+          out.push_back("  { " + m.residue_stmts(wm.first, "r") + fmt(" g[%d] = r; }", wm.first));
+          have.insert(wm.first);
+        }
+      out.push_back(fmt("  if ((%s) & 0x80808080u) return %du;", chunk_or(j, "g").c_str(), j));
+    }
+    for (int w = 0; w < W; w++)
+      if (!have.count(w)) out.push_back("  { " + m.residue_stmts(w, "r") + fmt(" g[%d] = r; }", w));
+  } else {
+    for (int w = 0; w < W; w++) out.push_back("  { " + m.residue_stmts(w, "r") + fmt(" g[%d] = r; }", w));
   }
   if (!m.rho_identity()) {
     for (int w = 0; w < W; w++) out.push_back(fmt("  g[%d] = %s;", w, m.g_from_r(w, fmt("g[%d]", w)).c_str()));

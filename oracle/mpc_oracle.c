@@ -9,7 +9,7 @@
  * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this file per block
  * against the unmodified reference compiled from /root/reference (oracle/_ref/libmpcref.so,
  * recipe oracle/build_ref.sh) and against the committed golden vectors in tests/golden/
- * (generated from that reference build by tools/make_golden.py).
+ * (generated from that reference build by tests/golden/make_golden.py).
  *
  * Every function cites the reference file:line it restates (paths relative to
  * /root/reference/src/compressor/).

@@ -17,7 +17,7 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle.bridge import REF_BIN, RefCompressor  # noqa: E402
 from tools.gen_dump import kat_blocks, synth  # noqa: E402

@@ -1,5 +1,5 @@
 """The drop-in CLI (bin/compressor + bin/run): CSV bytes and stdout must equal what the unmodified reference
-binary wrote for the same input (tests/golden/cli_*, produced by tools/make_golden.py)."""
+binary wrote for the same input (tests/golden/cli_*, produced by tests/golden/make_golden.py)."""
 import ctypes
 import os
 import subprocess
@@ -120,7 +120,7 @@ def test_bin_run_walks_the_dataset_like_the_reference(tmp_path, golden):
 @pytest.mark.parametrize("alg", ["BDI", "FPC", "BPC", "CPACK", "SC2"])
 def test_variant_csv_bytes_equal_reference(tmp_path, alg):
     """BASELINE config #5 through the drop-in CLI: same CSV row and stdout as the reference binary on the same dump
-    (tests/golden/cli_<ALG>_*, generated by tools/make_golden.py from the unmodified reference)."""
+    (tests/golden/cli_<ALG>_*, generated by tests/golden/make_golden.py from the unmodified reference)."""
     _build()
     from tools.gen_dump import synth
     ds = tmp_path / "ds"

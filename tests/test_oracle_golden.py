@@ -1,5 +1,5 @@
 """Pins the CPU oracle (oracle/mpc_oracle.c) to the reference: committed golden vectors generated from the
-unmodified reference build (tools/make_golden.py) and the known answers of SURVEY.md section 8c."""
+unmodified reference build (tests/golden/make_golden.py) and the known answers of SURVEY.md section 8c."""
 import numpy as np
 import pytest
 
