@@ -487,8 +487,9 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   if (t.use_lut && !((e = getenv("MPC_SPEC_LUTXOR")) && e[0] == '0')) t.lut_xor = all_c ? 1 : (!any_c ? 2 : 0);
   t.warps = (t.use_lut && !has_pm) ? 16 : 8;
   t.min_ctas = has_pm ? 1 : 2;
-  if ((e = getenv("MPC_SPEC_MIN_CTAS")) && atoi(e) > 0) t.min_ctas = atoi(e);
   if (t.warps == 16) t.min_ctas = 1;
+  if ((e = getenv("MPC_SPEC_WARPS")) && atoi(e) > 0) t.warps = atoi(e);        // tuning overrides
+  if ((e = getenv("MPC_SPEC_MIN_CTAS")) && atoi(e) > 0) t.min_ctas = atoi(e);
   e = getenv("MPC_SPEC_SKIP");
   t.skip_zero_groups = e ? (e[0] != '0') : !t.use_lut;
   t.smem_bytes = (size_t)t.warps * 2 * 4096 + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
