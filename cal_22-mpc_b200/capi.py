@@ -60,7 +60,7 @@ SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config
            "mpc_submit_device", "mpc_submit_host", "mpc_sync", "mpc_stats_device_ptr", "mpc_finish",
            "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version",
            "mpc_variant_run_device", "mpc_variant_run_host", "mpc_variant_error", "mpc_sc2_run_device", "mpc_sc2_run_host",
-           "mpc_sc2_error", "mpc_cpack_run_host", "mpc_jit_compile_check"]
+           "mpc_sc2_error", "mpc_cpack_run_host", "mpc_jit_compile_check", "mpc_enable_timing"]
 
 
 def lib():
@@ -83,6 +83,7 @@ def lib():
     l.mpc_set_kernel.argtypes = [vp, C.c_int]
     l.mpc_kernel_name.argtypes = [vp]
     l.mpc_set_stream.argtypes = [vp, vp]
+    l.mpc_enable_timing.argtypes = [vp, C.c_int]
     l.mpc_jit_compile_check.argtypes = [C.POINTER(ConfigPod), C.c_char_p, sz, C.POINTER(sz)]
     l.mpc_kernel_name.restype = C.c_char_p
     l.mpc_submit_device.argtypes = [vp, vp, u64, vp]
@@ -185,6 +186,9 @@ class Mpc:
 
     def set_stream(self, cuda_stream):
         self._check(lib().mpc_set_stream(self.h, cuda_stream))
+
+    def enable_timing(self, enabled):
+        self._check(lib().mpc_enable_timing(self.h, 1 if enabled else 0))
 
     def kernel_name(self):
         return lib().mpc_kernel_name(self.h).decode()

@@ -53,6 +53,7 @@ struct mpc_ctx {
   float last_ms = 0.f;
   int last_launches = 0;
   bool last_timing_pending = false;       // ev_start/ev_stop recorded but not read yet
+  bool timing_enabled = true;             // record the two events around mpc_submit_device launches
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_host_events;
   std::string error;
   std::string kernel_name;
@@ -265,6 +266,12 @@ int mpc_jit_compile_check(const mpc_config_pod* cfg, char* log, size_t log_len, 
   return rc;
 }
 
+int mpc_enable_timing(mpc_ctx* ctx, int enabled) {
+  if (!ctx) return MPC_E_ARG;
+  ctx->timing_enabled = enabled != 0;
+  return MPC_OK;
+}
+
 int mpc_set_stream(mpc_ctx* ctx, void* cuda_stream) {
   if (!ctx) return MPC_E_ARG;
   int rc = mpc_sync(ctx);
@@ -278,11 +285,12 @@ int mpc_submit_device(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n_blocks, u
   if (n_blocks && !d_lines) return fail(ctx, MPC_E_ARG, "mpc_submit_device: null lines");
   if ((uintptr_t)d_lines & 15) return fail(ctx, MPC_E_ARG, "mpc_submit_device: lines must be 16-byte aligned");
   MPC_CUDA(ctx, cudaSetDevice(ctx->device));
-  MPC_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+  if (ctx->timing_enabled) MPC_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
   int rc = n_blocks ? launch(ctx, d_lines, n_blocks, d_packed, ctx->stream) : MPC_OK;
   if (rc != MPC_OK) return rc;
-  MPC_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
-  ctx->last_timing_pending = true;
+  if (ctx->timing_enabled) MPC_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+  ctx->last_timing_pending = ctx->timing_enabled;
+  if (!ctx->timing_enabled) ctx->last_ms = 0.f;
   ctx->last_launches = n_blocks ? 1 : 0;
   return MPC_OK;
 }

@@ -146,6 +146,10 @@ int mpc_reset(mpc_ctx* ctx);
  * mpc_submit_device / mpc_submit_host call, and the number of kernel launches it made. */
 int mpc_last_timing(mpc_ctx* ctx, float* kernel_ms, int* launches);
 
+/* mpc_submit_device brackets its launch with two CUDA events for mpc_last_timing; a caller that times a train of
+ * back-to-back launches itself can switch them off (enabled = 0) to keep the stream free of extra commands. */
+int mpc_enable_timing(mpc_ctx* ctx, int enabled);
+
 /* ---- synthetic dumps (BASELINE.json configs; generator shared with tools/gen_dump.py) ---- */
 
 enum {
