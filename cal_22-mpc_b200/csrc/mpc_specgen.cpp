@@ -54,6 +54,8 @@ std::string join(const std::vector<std::string>& v, const char* sep) {
   return s;
 }
 
+typedef std::vector<std::string> Lines;
+
 // ---- byte-gather planning ---------------------------------------------------------------------------------------
 // Expression for a 32-bit word whose byte q is byte srcs[q] of the 128-byte array `arr` (available as arr[0..31]),
 // or zero when srcs[q] < 0.
@@ -252,14 +254,110 @@ struct Module {
   }
 };
 
-typedef std::vector<std::string> Lines;
+// ---- row layout of column-major modules -----------------------------------------------------------------------------
+// The encoder reads 32 words of two 16-bit scan rows each.  Legacy layout: word j = rows 2j, 2j+1 -- one byte from each
+// of up to four residue words, i.e. three PRMTs per word.  Paired layout: word j = rows (ra[j], rb[j]) chosen so that
+// the four bytes come from at most two residue words (ONE PRMT); the non-zero flags of the rows are then accumulated per
+// "run" (words whose ra and rb both advance by one) and shifted into place in the 64-bit zero-row mask at the end.
+struct RowLayout {
+  bool paired = false;
+  int ra[W], rb[W];      // rows in the low / high halfword of word j
+  int grp[W], slot[W];   // flag accumulator of word j and its bit position in it
+  struct Group { int A, B, len; };
+  std::vector<Group> groups;
+};
+
+int count_prmts(const std::string& e) {
+  int n = 0;
+  for (size_t pos = e.find("prmt("); pos != std::string::npos; pos = e.find("prmt(", pos + 1)) n++;
+  return n;
+}
+
+// srcs of encoder word holding rows (a, b) of a module with scan columns `cols` (resized to L, -1 = no column)
+void row_pair_srcs(const std::vector<int>& cols, int a, int b, int (&srcs)[4]) {
+  srcs[0] = cols[2 * a + 1]; srcs[1] = cols[2 * a]; srcs[2] = cols[2 * b + 1]; srcs[3] = cols[2 * b];
+}
+
+RowLayout plan_row_layout(const std::vector<std::vector<int>>& cm_cols) {
+  RowLayout lay;
+  for (int j = 0; j < W; j++) { lay.ra[j] = 2 * j; lay.rb[j] = 2 * j + 1; lay.grp[j] = 0; lay.slot[j] = 0; }
+  if (cm_cols.empty()) return lay;
+  const std::vector<int>& cols = cm_cols[0];
+  auto words_of = [&](int r) {
+    std::set<int> w;
+    for (int c : {cols[2 * r], cols[2 * r + 1]})
+      if (c >= 0) w.insert(c / 4);
+    return w;
+  };
+  auto fits = [&](int a, int b) {
+    std::set<int> u = words_of(a), v = words_of(b);
+    u.insert(v.begin(), v.end());
+    return u.size() <= 2;
+  };
+  // rows that read the same pair of residue words are paired first (in row order), then any two rows that fit one PRMT
+  std::map<std::set<int>, std::vector<int>> buckets;
+  for (int r = 0; r < 64; r++) buckets[words_of(r)].push_back(r);
+  std::vector<std::pair<int, int>> pairs;
+  std::vector<int> left;
+  for (auto& kv : buckets) {
+    auto& v = kv.second;
+    size_t i = 0;
+    if (kv.first.size() == 2)
+      for (; i + 1 < v.size(); i += 2) pairs.push_back({v[i], v[i + 1]});
+    for (; i < v.size(); i++) left.push_back(v[i]);
+  }
+  std::sort(left.begin(), left.end());
+  std::vector<bool> used(left.size(), false);
+  for (size_t i = 0; i < left.size(); i++) {
+    if (used[i]) continue;
+    for (size_t k = i + 1; k < left.size(); k++)
+      if (!used[k] && fits(left[i], left[k])) { pairs.push_back({left[i], left[k]}); used[i] = used[k] = true; break; }
+  }
+  std::vector<int> rest;
+  for (size_t i = 0; i < left.size(); i++)
+    if (!used[i]) rest.push_back(left[i]);
+  for (size_t i = 0; i + 1 < rest.size(); i += 2) pairs.push_back({rest[i], rest[i + 1]});
+  if (pairs.size() != (size_t)W) return lay;
+  std::sort(pairs.begin(), pairs.end());
+  // PRMT count of both layouts over every column-major module of the config
+  int cost_legacy = 0, cost_paired = 0;
+  for (auto& mc : cm_cols)
+    for (int j = 0; j < W; j++) {
+      int s0[4], s1[4];
+      row_pair_srcs(mc, 2 * j, 2 * j + 1, s0);
+      row_pair_srcs(mc, pairs[j].first, pairs[j].second, s1);
+      cost_legacy += count_prmts(gather_expr("g", s0));
+      cost_paired += count_prmts(gather_expr("g", s1));
+    }
+  // runs: consecutive words whose two rows both advance by one share a flag accumulator (16 flags per halfword)
+  RowLayout p;
+  p.paired = true;
+  for (int j = 0; j < W; j++) {
+    p.ra[j] = pairs[j].first;
+    p.rb[j] = pairs[j].second;
+    if (j > 0 && p.ra[j] == p.ra[j - 1] + 1 && p.rb[j] == p.rb[j - 1] + 1 && p.groups.back().len < 16) {
+      p.groups.back().len++;
+    } else {
+      p.groups.push_back({p.ra[j], p.rb[j], 1});
+    }
+    p.grp[j] = (int)p.groups.size() - 1;
+    p.slot[j] = p.groups.back().len - 1;
+  }
+  const char* e = getenv("MPC_SPEC_PAIRED");
+  if (e && e[0] == '0') return lay;
+  if (p.groups.size() > 8 || cost_paired + 4 * (int)p.groups.size() >= cost_legacy) return lay;
+  return p;
+}
+
+// encode_rows: the row classifier for the paired layout (row-cost table in shared memory), emitted per config
+void emit_encode_rows(const RowLayout& lay, Lines& out);
 
 // full_<m>: all 32 residue words -> residue sums, canonical row layout c[32].
 // lut_xor != 0 (column-major modules only): the row-cost table is indexed with the residue bytes BEFORE the XOR stage --
 // the stage is a per-byte bijection (Gray code / conditional complement), so it is folded into the table and disappears
 // from the kernel; only the root byte, which the XOR stage skips (XORModule.cpp:12), is run through the inverse map so
 // that the table maps it back to itself.
-void emit_full(const Module& m, Lines& out, int lut_xor) {
+void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay) {
   out.push_back(fmt("__device__ __forceinline__ void full_%d(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq) {", m.idx));
   out.push_back("  uint32_t g[32];");
   out.push_back("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one");
@@ -294,7 +392,8 @@ void emit_full(const Module& m, Lines& out, int lut_xor) {
     std::vector<int> cols = m.cols;
     cols.resize(L, -1);
     for (int j = 0; j < W; j++) {
-      const int srcs[4] = {cols[4 * j + 1], cols[4 * j], cols[4 * j + 3], cols[4 * j + 2]};
+      int srcs[4];
+      row_pair_srcs(cols, lay.ra[j], lay.rb[j], srcs);  // legacy layout: rows 2j, 2j+1
       out.push_back(fmt("  c[%d] = %s;", j, gather_expr("g", srcs).c_str()));
     }
   } else {
@@ -306,6 +405,26 @@ void emit_full(const Module& m, Lines& out, int lut_xor) {
       }
   }
   out.push_back("}");
+}
+
+void emit_encode_rows(const RowLayout& lay, Lines& out) {
+  out.push_back("// Row classifier for the paired row layout: word j holds scan rows ra (low halfword) and rb (high halfword); each row");
+  out.push_back("// costs one table load; the non-zero flags of a run of words land in one accumulator and are shifted into the 64-bit");
+  out.push_back("// row mask at the end (zero runs: FPCModule.cpp:27-45, 69-79).");
+  out.push_back("__device__ __forceinline__ uint32_t encode_rows(const uint32_t (&c)[32], const uint8_t* __restrict__ lut) {");
+  out.push_back("  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;");
+  std::vector<std::string> ns;
+  for (size_t g = 0; g < lay.groups.size(); g++) ns.push_back(fmt("n%d = 0", (int)g));
+  out.push_back("  uint32_t " + join(ns, ", ") + ";");
+  for (int j = 0; j < W; j++)
+    out.push_back(fmt("  row_pair_step(c[%d], lut, a%d, a%d, n%d, 0x%xu);  // rows %d, %d", j, (j & 1) * 2, (j & 1) * 2 + 1, lay.grp[j],
+                      1u << lay.slot[j], lay.ra[j], lay.rb[j]));
+  out.push_back("  uint64_t nzm = 0;");
+  for (size_t g = 0; g < lay.groups.size(); g++)
+    out.push_back(fmt("  nzm |= ((uint64_t)(n%d & 0xffffu) << %d) | ((uint64_t)(n%d >> 16) << %d);", (int)g, lay.groups[g].A, (int)g, lay.groups[g].B));
+  out.push_back("  return (a0 + a1) + (a2 + a3) + mpcdev::zero_run_cost(~nzm);");
+  out.push_back("}");
+  out.push_back("");
 }
 
 // Leading zero rows of a column-major module.  A scan row is two bytes of the XOR-ed residue line, and such a byte is
@@ -522,11 +641,19 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   out.push_back("template <class F> __device__ __forceinline__ uint32_t shiftmix(uint32_t p, F f) { return f(p); }");
   out.push_back("");
   static const char* kPredNames[] = {"OneBasePredictor", "ConsecutiveBasePredictor", "DiffBasePredictor", "WeightBasePredictor"};
+  RowLayout lay;
+  {
+    std::vector<std::vector<int>> cm_cols;
+    for (auto& m : mods)
+      if (m.family == Module::kCm) { cm_cols.push_back(m.cols); cm_cols.back().resize(L, -1); }
+    lay = plan_row_layout(t.use_lut ? cm_cols : std::vector<std::vector<int>>());
+  }
+  if (lay.paired) emit_encode_rows(lay, out);
   for (auto& m : mods) {
     out.push_back(fmt("// ---- module %d: %s, root %d, %s XOR, %s-major scan ----", m.idx, kPredNames[m.predictor], m.root,
                       m.cxor ? "consecutive" : "first-plane", m.family == Module::kCm ? "column" : "plane"));
     if (m.family == Module::kCm) emit_score_cm(m, out); else emit_score_pm(m, out);
-    emit_full(m, out, t.lut_xor);
+    emit_full(m, out, t.lut_xor, lay);
     out.push_back("");
   }
   out.push_back("struct Cfg {");
@@ -583,7 +710,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   out.push_back("    }");
   out.push_back("    __syncwarp(lanes);  // the row classifier below is shared by all modules: run it once per warp");
   auto call = [&](const std::pair<int, std::pair<unsigned, unsigned>>& f) {
-    return f.first == 0 ? std::string("encode_cm<kUseLut, kSkipZeroGroups>(c, lut)")
+    return f.first == 0 ? std::string(lay.paired ? "encode_rows(c, lut)" : "encode_cm<kUseLut, kSkipZeroGroups>(c, lut)")
                         : fmt("encode_pm<0x%04xu, 0x%04xu>(c)", f.second.first, f.second.second);
   };
   if (fams.size() == 1) {
