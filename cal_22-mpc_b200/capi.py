@@ -52,7 +52,8 @@ class MpcError(RuntimeError):
 
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpc_b200.so")
+# MPC_B200_LIB: another build of the same library (A/B runs of two kernel versions on one GPU box)
+LIB_PATH = os.environ.get("MPC_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpc_b200.so")
 
 # every symbol include/mpc_capi.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config_validate", "mpc_create",

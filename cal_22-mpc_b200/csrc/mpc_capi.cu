@@ -45,6 +45,7 @@ struct mpc_ctx {
   mpc::JitKernel* jit = nullptr;          // specialised kernel built at run time (NVRTC) when none is compiled in
   int kernel_choice = 0;
   uint64_t* d_stats = nullptr;
+  uint32_t* d_sched = nullptr;            // tile-scheduler words of the specialised kernels: 3 slots (device stream, 2 stages) x 32 words
   cudaStream_t own_stream = nullptr;      // created by mpc_create
   cudaStream_t stream = nullptr;          // stream used by mpc_submit_device / synth / stats (own or caller's)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_order = nullptr;
@@ -89,12 +90,15 @@ void refresh_kernel_name(mpc_ctx* ctx) {
   else ctx->kernel_name = std::string("spec_thread:") + (ctx->spec ? ctx->spec->name : "jit");
 }
 
-int launch(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n, uint16_t* d_packed, cudaStream_t s) {
+// `slot` names the scheduler words the launch uses: launches that may overlap (the two stages of mpc_submit_host) must
+// not share them; launches on one stream run one after the other and the kernel leaves its slot zeroed.
+int launch(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n, uint16_t* d_packed, cudaStream_t s, int slot) {
   cudaError_t e;
+  uint32_t* sched = ctx->d_sched + 32 * slot;
   if (use_spec(ctx) && ctx->spec)
-    e = ctx->spec->launch(ctx->cfg, d_lines, n, d_packed, ctx->d_stats, ctx->d_row_lut, ctx->sm_count, s);
+    e = ctx->spec->launch(ctx->cfg, d_lines, n, d_packed, ctx->d_stats, ctx->d_row_lut, sched, ctx->sm_count, s);
   else if (use_spec(ctx))
-    e = mpc::jit_launch(ctx->jit, d_lines, n, d_packed, ctx->d_stats, ctx->d_row_lut, ctx->sm_count, s);
+    e = mpc::jit_launch(ctx->jit, d_lines, n, d_packed, ctx->d_stats, ctx->d_row_lut, sched, ctx->sm_count, s);
   else
     e = mpc::launch_generic(ctx->gparams, ctx->d_gmods, d_lines, n, d_packed, ctx->d_stats, ctx->sm_count, s);
   if (e != cudaSuccess) return fail(ctx, MPC_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -186,6 +190,8 @@ int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out) {
   MPC_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
   MPC_CREATE_CUDA(cudaMalloc(&ctx->d_stats, mpc::kStatsWords * sizeof(uint64_t)));
   MPC_CREATE_CUDA(cudaMemsetAsync(ctx->d_stats, 0, mpc::kStatsWords * sizeof(uint64_t), ctx->stream));
+  MPC_CREATE_CUDA(cudaMalloc(&ctx->d_sched, 3 * 32 * sizeof(uint32_t)));
+  MPC_CREATE_CUDA(cudaMemsetAsync(ctx->d_sched, 0, 3 * 32 * sizeof(uint32_t), ctx->stream));
   std::vector<mpc::GenericModule> gm((size_t)MPC_MAX_MODULES);
   mpc::build_generic_tables(ctx->cfg, &ctx->gparams, gm.data());
   const size_t gbytes = sizeof(mpc::GenericModule) * (size_t)(ctx->gparams.num_predcomp > 0 ? ctx->gparams.num_predcomp : 1);
@@ -236,6 +242,7 @@ void mpc_destroy(mpc_ctx* ctx) {
   if (ctx->d_row_lut) cudaFree(ctx->d_row_lut);
   if (ctx->jit) mpc::jit_destroy(ctx->jit);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->d_sched) cudaFree(ctx->d_sched);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
   if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
@@ -286,7 +293,7 @@ int mpc_submit_device(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n_blocks, u
   if ((uintptr_t)d_lines & 15) return fail(ctx, MPC_E_ARG, "mpc_submit_device: lines must be 16-byte aligned");
   MPC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->timing_enabled) MPC_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
-  int rc = n_blocks ? launch(ctx, d_lines, n_blocks, d_packed, ctx->stream) : MPC_OK;
+  int rc = n_blocks ? launch(ctx, d_lines, n_blocks, d_packed, ctx->stream, 0) : MPC_OK;
   if (rc != MPC_OK) return rc;
   if (ctx->timing_enabled) MPC_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
   ctx->last_timing_pending = ctx->timing_enabled;
@@ -327,7 +334,7 @@ int mpc_submit_host(mpc_ctx* ctx, const uint8_t* h_lines, uint64_t n_blocks, uin
       MPC_CUDA(ctx, cudaMemcpyAsync(st.d_lines, st.h_pinned, nb * L, cudaMemcpyHostToDevice, st.stream));
     }
     MPC_CUDA(ctx, cudaEventRecord(st.k_start, st.stream));
-    rc = launch(ctx, st.d_lines, nb, h_packed ? st.d_packed : nullptr, st.stream);
+    rc = launch(ctx, st.d_lines, nb, h_packed ? st.d_packed : nullptr, st.stream, 1 + which);
     if (rc != MPC_OK) return rc;
     MPC_CUDA(ctx, cudaEventRecord(st.k_stop, st.stream));
     ctx->last_launches++;
@@ -405,6 +412,7 @@ int mpc_reset(mpc_ctx* ctx) {
   int rc = mpc_sync(ctx);
   if (rc != MPC_OK) return rc;
   MPC_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, mpc::kStatsWords * sizeof(uint64_t), ctx->stream));
+  MPC_CUDA(ctx, cudaMemsetAsync(ctx->d_sched, 0, 3 * 32 * sizeof(uint32_t), ctx->stream));
   MPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MPC_OK;
 }

@@ -150,14 +150,20 @@ void jit_destroy(JitKernel* k) {
 int jit_lut_xor(const JitKernel* k) { return k->traits.use_lut ? k->traits.lut_xor : 0; }
 
 cudaError_t jit_launch(JitKernel* k, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed, uint64_t* d_stats,
-                       const uint8_t* d_row_lut, int sm_count, cudaStream_t stream) {
+                       const uint8_t* d_row_lut, uint32_t* d_sched, int sm_count, cudaStream_t stream) {
   if (n_blocks == 0) return cudaSuccess;
   const uint64_t n_tiles = (n_blocks + 31) / 32;
   uint64_t grid = (uint64_t)sm_count * k->per_sm;
   const uint64_t want = (n_tiles + k->traits.warps - 1) / k->traits.warps;
   if (grid > want) grid = want;
   unsigned long long n = n_blocks;
-  void* args[] = {(void*)&d_lines, (void*)&n, (void*)&d_packed, (void*)&d_stats, (void*)&d_row_lut};
+  const char* e = getenv("MPC_SCHED_STATIC_EIGHTHS");
+  int eighths = e ? atoi(e) : 7;
+  eighths = eighths < 0 ? 0 : (eighths > 8 ? 8 : eighths);
+  const uint64_t total_warps = grid * (uint64_t)k->traits.warps;
+  unsigned int static_rounds = eighths == 8 ? (unsigned int)((n_tiles + total_warps - 1) / total_warps)
+                                            : (unsigned int)((n_tiles / total_warps) * (uint64_t)eighths / 8);
+  void* args[] = {(void*)&d_lines, (void*)&n, (void*)&d_packed, (void*)&d_stats, (void*)&d_row_lut, (void*)&d_sched, (void*)&static_rounds};
   CUresult r = driver().LaunchKernel(k->fn, (unsigned)grid, 1, 1, (unsigned)(k->traits.warps * 32), 1, 1,
                                      (unsigned)k->traits.smem_bytes, (CUstream)stream, args, nullptr);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;

@@ -19,6 +19,6 @@ JitKernel* jit_create(const mpc_config_pod& cfg, std::string* log);
 void jit_destroy(JitKernel* k);
 int jit_lut_xor(const JitKernel* k);
 cudaError_t jit_launch(JitKernel* k, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed, uint64_t* d_stats,
-                       const uint8_t* d_row_lut, int sm_count, cudaStream_t stream);
+                       const uint8_t* d_row_lut, uint32_t* d_sched, int sm_count, cudaStream_t stream);
 
 }  // namespace mpc

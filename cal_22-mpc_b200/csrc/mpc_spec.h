@@ -12,7 +12,7 @@ struct SpecKernel {
   // true when `cfg` is exactly the config the kernel was compiled for
   bool (*matches)(const mpc_config_pod& cfg);
   cudaError_t (*launch)(const mpc_config_pod& cfg, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed,
-                        uint64_t* d_stats, const uint8_t* d_row_lut, int sm_count, cudaStream_t stream);
+                        uint64_t* d_stats, const uint8_t* d_row_lut, uint32_t* d_sched, int sm_count, cudaStream_t stream);
   int lut_xor;  // which row-cost table the kernel expects (0 plain, 1 consecutive-XOR folded in, 2 first-plane-XOR folded in)
 };
 

@@ -729,8 +729,9 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     out.push_back("}  // namespace mpc");
     out.push_back(fmt("extern \"C\" __global__ void __launch_bounds__(mpc::spec_%s::Cfg::kWarps * 32, mpc::spec_%s::Cfg::kMinCtasPerSm)", name.c_str(), name.c_str()));
     out.push_back("mpc_jit_kernel(const uint4* __restrict__ lines, unsigned long long n_blocks, unsigned short* __restrict__ packed,");
-    out.push_back("               unsigned long long* __restrict__ stats, const uint4* __restrict__ row_lut) {");
-    out.push_back(fmt("  mpc::spec::spec_kernel_body<mpc::spec_%s::Cfg>(lines, n_blocks, packed, stats, row_lut);", name.c_str()));
+    out.push_back("               unsigned long long* __restrict__ stats, const uint4* __restrict__ row_lut, unsigned int* __restrict__ sched,");
+    out.push_back("               unsigned int static_rounds) {");
+    out.push_back(fmt("  mpc::spec::spec_kernel_body<mpc::spec_%s::Cfg>(lines, n_blocks, packed, stats, row_lut, sched, static_rounds);", name.c_str()));
     out.push_back("}");
   } else {
     out.push_back("static const mpc_config_pod kPod =");
@@ -738,8 +739,8 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     out.push_back("");
     out.push_back("static bool matches(const mpc_config_pod& cfg) { return spec_pod_equal(cfg, kPod); }");
     out.push_back("static cudaError_t launch(const mpc_config_pod&, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed,");
-    out.push_back("                          uint64_t* d_stats, const uint8_t* d_row_lut, int sm_count, cudaStream_t stream) {");
-    out.push_back("  return launch_spec<Cfg>(d_lines, n_blocks, d_packed, d_stats, d_row_lut, sm_count, stream);");
+    out.push_back("                          uint64_t* d_stats, const uint8_t* d_row_lut, uint32_t* d_sched, int sm_count, cudaStream_t stream) {");
+    out.push_back("  return launch_spec<Cfg>(d_lines, n_blocks, d_packed, d_stats, d_row_lut, d_sched, sm_count, stream);");
     out.push_back("}");
     out.push_back(fmt("}  // namespace spec_%s", name.c_str()));
     out.push_back(fmt("extern const SpecKernel kSpec_%s = {\"%s\", spec_%s::matches, spec_%s::launch, spec_%s::Cfg::kLutXor};", name.c_str(),

@@ -15,9 +15,10 @@
 int main(int argc, char** argv) {
   const uint64_t n = argc > 1 ? strtoull(argv[1], 0, 10) : (1ull << 23);
   const int kind = argc > 2 ? atoi(argv[2]) : 2;
-  uint8_t* d; uint64_t* st; uint8_t* lut;
+  uint8_t* d; uint64_t* st; uint8_t* lut; uint32_t* sched;
   CK(cudaMalloc(&d, n * 128)); CK(cudaMalloc(&st, mpc::kStatsWords * 8)); CK(cudaMalloc(&lut, 65536));
   CK(cudaMemset(st, 0, mpc::kStatsWords * 8));
+  CK(cudaMalloc(&sched, 128)); CK(cudaMemset(sched, 0, 128));
   std::vector<uint8_t> h(65536);
   mpc::build_row_cost_lut(h.data(), mpc::spec_F4::Cfg::kLutXor);
   CK(cudaMemcpy(lut, h.data(), 65536, cudaMemcpyHostToDevice));
@@ -27,7 +28,7 @@ int main(int argc, char** argv) {
   mpc_config_pod* pod = new mpc_config_pod();
   for (int it = 0; it < 4; it++) {
     cudaEventRecord(e0);
-    CK(mpc::kSpec_F4.launch(*pod, d, n, nullptr, st, lut, p.multiProcessorCount, 0));
+    CK(mpc::kSpec_F4.launch(*pod, d, n, nullptr, st, lut, sched, p.multiProcessorCount, 0));
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
