@@ -604,14 +604,19 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   t.use_lut = has_cm && !((e = getenv("MPC_SPEC_LUT")) && e[0] == '0');
   t.lut_xor = 0;
   if (t.use_lut && !((e = getenv("MPC_SPEC_LUTXOR")) && e[0] == '0')) t.lut_xor = all_c ? 1 : (!any_c ? 2 : 0);
-  t.warps = (t.use_lut && !has_pm) ? 16 : 8;
+  // column-major only: ONE CTA of 20 warps per SM at 96 registers (the next allocation step down, 80, spills), one
+  // 4 KiB tile stage per warp; measured on B200: 16 warps x 2 stages 4.11 TB/s, 18 x 1 4.16, 20 x 1 4.26, 21/22/24 x 1 (80
+  // registers) 3.86-3.93 on the headline workload
+  t.warps = (t.use_lut && !has_pm) ? 20 : 8;
+  t.stages = (t.use_lut && !has_pm) ? 1 : 2;
   t.min_ctas = has_pm ? 1 : 2;
-  if (t.warps == 16) t.min_ctas = 1;
-  if ((e = getenv("MPC_SPEC_WARPS")) && atoi(e) > 0) t.warps = atoi(e);        // tuning overrides
+  if (t.warps >= 16) t.min_ctas = 1;
+  if ((e = getenv("MPC_SPEC_WARPS")) && atoi(e) > 0) { t.warps = atoi(e); t.min_ctas = t.warps >= 16 ? 1 : t.min_ctas; }  // tuning overrides
   if ((e = getenv("MPC_SPEC_MIN_CTAS")) && atoi(e) > 0) t.min_ctas = atoi(e);
   e = getenv("MPC_SPEC_SKIP");
   t.skip_zero_groups = e ? (e[0] != '0') : !t.use_lut;
-  t.smem_bytes = (size_t)t.warps * 2 * 4096 + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
+  if ((e = getenv("MPC_SPEC_STAGES")) && (atoi(e) == 1 || atoi(e) == 2)) t.stages = atoi(e);
+  t.smem_bytes = (size_t)t.warps * t.stages * 4096 + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
                  (t.use_lut ? 65536 : 0);
   return t;
 }
@@ -664,6 +669,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   // column-major only: 16 warps in ONE CTA per SM (<= 128 registers) so that the 64 KiB row-cost table, the 128 KiB of
   // tile stages and the histogram fit the 227 KiB of shared memory
   out.push_back(fmt("  static constexpr int kWarps = %d;", t.warps));
+  out.push_back(fmt("  static constexpr int kStages = %d;  // shared-memory tile stages per warp", t.stages));
   out.push_back(fmt("  static constexpr bool kUseLut = %s;  // shared-memory row-cost table (column-major modules)", t.use_lut ? "true" : "false"));
   out.push_back(fmt("  static constexpr bool kSkipZeroGroups = %s;  // branch around groups of eight zero rows in the encoder", t.skip_zero_groups ? "true" : "false"));
   out.push_back(fmt("  static constexpr int kLutXor = %d;  // 0: table indexed by scan rows; 1 / 2: XOR stage (consecutive / first-plane) folded into the table",

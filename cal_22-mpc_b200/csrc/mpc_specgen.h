@@ -12,6 +12,7 @@ struct SpecTraits {
   bool use_lut = false;          // column-major modules: 64 KiB shared-memory row-cost table
   int lut_xor = 0;               // 0 plain table, 1 / 2: consecutive / first-plane XOR stage folded into the table
   int warps = 8;                 // warps per CTA
+  int stages = 2;                // shared-memory tile stages per warp (1: the registers are the second buffer)
   int min_ctas = 2;              // __launch_bounds__ second argument
   bool skip_zero_groups = true;  // encoder branches around groups of eight zero rows
   size_t smem_bytes = 0;         // dynamic shared memory of one CTA

@@ -1,9 +1,10 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_jit.py -m gpu -x -q 2>&1 | tail -2
-for i in 1 2; do
-MPC_B200_LIB=$PWD/cal_22-mpc_b200/libmpc_b200_prev.so bash tools/quickbench.sh F4smooth_prev
-MPC_SCHED_STATIC_EIGHTHS=8 bash tools/quickbench.sh F4smooth_static8
-MPC_SCHED_STATIC_EIGHTHS=7 bash tools/quickbench.sh F4smooth_static7
-MPC_SCHED_STATIC_EIGHTHS=6 bash tools/quickbench.sh F4smooth_static6
-done
-MPC_B200_LIB=$PWD/cal_22-mpc_b200/libmpc_b200_prev.so bash tools/quickbench.sh F4smooth4G_prev --bytes-per-gpu 4294967296
-MPC_SCHED_STATIC_EIGHTHS=7 bash tools/quickbench.sh F4smooth4G_static7 --bytes-per-gpu 4294967296
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+bash tools/quickbench.sh F4smooth
+bash tools/quickbench.sh F4mixed --kind mixed_hashed
+bash tools/quickbench.sh Z1mixed --config Z1 --kind mixed_hashed
+bash tools/quickbench.sh Z1smooth --config Z1
+bash tools/quickbench.sh E5mixed --config E5 --kind mixed_hashed
+bash tools/quickbench.sh P6mixed --config P6 --kind mixed_hashed
+bash tools/quickbench.sh P6smooth --config P6
+bash tools/quickbench.sh F4zero --kind zero
+bash tools/quickbench.sh F4smooth4G --bytes-per-gpu 4294967296
