@@ -13,13 +13,14 @@
 
 #include "compressor/VPC.h"
 #include "compressor/Variants.h"
+#include "loader/LoaderGPGPU.h"
 #include "loader/LoaderNPY.h"
 #include "utils.h"
 
 static const char* kHelp =
     "\nUsage:\n  Compressor [OPTION...]\n\n"
-    "  -a, --algorithm arg  Compression algorithm [VPC/FPC/BDI/BPC/CPACK/SC2]. Default=VPC\n"
-    "  -i, --input arg      Input memory dump path. Supported extensions: .npy\n"
+    "  -a, --algorithm arg  Compression algorithm [VPC/FPC/BDI/BPC/CPACK/SC2/VIEWER]. Default=VPC\n"
+    "  -i, --input arg      Input path. Supported extensions: .npy (memory dump), .log (GPGPU-Sim trace)\n"
     "  -c, --config arg     Config file path (.json).\n"
     "  -o, --output arg     Output directory path\n"
     "      --gpus arg       Number of GPUs to shard the dump over (default 1)\n"
@@ -28,6 +29,7 @@ static const char* kHelp =
     "  -h, --help           Print usage\n";
 
 comp::CompResult* compressLines(comp::Compressor* compressor, trace::Loader* loader, unsigned lineSize);
+void viewLines(trace::Loader* loader);
 
 int main(int argc, char** argv) {
   std::string algorithm = "VPC", tracePath, configPath, outputDirPath;
@@ -57,9 +59,13 @@ int main(int argc, char** argv) {
     trace::LoaderNPY* l = new trace::LoaderNPY(tracePath);
     if (!l->Error().empty()) { printf("%s\n", l->Error().c_str()); return 1; }
     loader = l;
+  } else if (endsWith(tracePath, ".log")) {
+    trace::gpgpusim::LoaderGPGPU* l = new trace::gpgpusim::LoaderGPGPU(tracePath);  // main.cpp:76-77
+    if (!l->Error().empty()) { printf("%s\n", l->Error().c_str()); return 1; }
+    loader = l;
   } else {
-    // .log (GPGPU-Sim traces) and .txt (AXI dumps) are outside the GPU hot path
-    printf("Unsupported extension: \"%s\" (this build reads .npy memory dumps)\n", tracePath.c_str());
+    // .txt (AXI channel dumps of the reference's apsim loader) is outside the GPU hot path
+    printf("Unsupported extension: \"%s\" (this build reads .npy memory dumps and .log GPGPU-Sim traces)\n", tracePath.c_str());
     return 1;
   }
   const unsigned lineSize = loader->GetCachelineSize();  // main.cpp:86
@@ -69,9 +75,12 @@ int main(int argc, char** argv) {
     compressor = new comp::VPC(configPath, gpus, kernel);  // main.cpp:88-91
   } else if (algorithm == "BDI" || algorithm == "FPC" || algorithm == "BPC" || algorithm == "CPACK" || algorithm == "SC2") {
     compressor = new comp::VariantCompressor(algorithm, lineSize, loader->GetNumLines());  // main.cpp:92-116
+  } else if (algorithm == "VIEWER") {
+    viewLines(loader);  // main.cpp:121-125: host only, no compressor
+    return 0;
   } else {
-    // PATTERN (analysis tool, ratio always 0) and VIEWER are outside the compression path
-    printf("Invalid name of algorithm: \"%s\" (this build implements VPC, BDI, FPC, BPC, CPACK, SC2)\n", algorithm.c_str());
+    // PATTERN (analysis tool, ratio always 0) is outside the compression path
+    printf("Invalid name of algorithm: \"%s\" (this build implements VPC, BDI, FPC, BPC, CPACK, SC2, VIEWER)\n", algorithm.c_str());
     return 1;
   }
 
@@ -119,4 +128,27 @@ comp::CompResult* compressLines(comp::Compressor* compressor, trace::Loader* loa
     while ((n = loader->GetChunk(buf.data(), chunkLines)) != 0) compressor->CompressBatch(buf.data(), n);
   }
   return compressor->GetResult();
+}
+
+// main.cpp:250-300: hex dump of the lines compressLines would see; GPGPU-Sim records carry an R:/W: prefix
+void viewLines(trace::Loader* loader) {
+  if (dynamic_cast<trace::gpgpusim::LoaderGPGPU*>(loader) != nullptr) {
+    trace::gpgpusim::MemReqGPU_t req;
+    while (1) {
+      loader->GetCacheline(&req);
+      if (req.isEnd) break;
+      if (!(req.reqType == trace::gpgpusim::GLOBAL_ACC_R || req.reqType == trace::gpgpusim::GLOBAL_ACC_W)) continue;
+      printf("%s: ", req.reqType == trace::gpgpusim::GLOBAL_ACC_R ? "R" : "W");
+      for (size_t i = 0; i < req.data.size(); i++) printf("%02x ", req.data[i]);
+      printf("\n");
+    }
+  } else {
+    trace::MemReq_t req;
+    while (1) {
+      loader->GetCacheline(&req);
+      if (req.isEnd) break;
+      for (size_t i = 0; i < req.data.size(); i++) printf("%02x ", req.data[i]);
+      printf("\n");
+    }
+  }
 }

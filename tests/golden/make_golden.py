@@ -20,7 +20,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle.bridge import REF_BIN, RefCompressor  # noqa: E402
-from tools.gen_dump import kat_blocks, synth  # noqa: E402
+from tools.gen_dump import kat_blocks, synth, write_gpgpusim_log  # noqa: E402
 
 CONFIGS = ["P6", "F4", "Z1", "E5"]
 
@@ -65,6 +65,13 @@ def golden_blocks():
     return np.concatenate([blocks, pad])
 
 
+def gpgpusim_case():
+    """Blocks and request types of the .log fixture (shared with tests/test_loader_gpgpu.py)."""
+    blocks = golden_blocks()[:330]
+    types = [(0, 4, 1, 0, 8, 4, 2, 0, 6, 5, 3, 0, 7)[i % 13] for i in range(len(blocks))]
+    return blocks, types
+
+
 def main():
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
@@ -103,6 +110,30 @@ def main():
             with open(os.path.join(gold, f"cli_{cfg}_stdout.txt"), "w") as g:
                 g.write(stdout)
             print(cfg, "cli:", stdout.strip())
+        # GPGPU-Sim trace (.log) through the reference CLI: 330 records of mixed request types (only GLOBAL_ACC_R/W are
+        # compressed, main.cpp:222-224), the last record cut short (dropped: LoaderGPGPU.cpp:46-52)
+        import hashlib
+        import json
+        log_blocks, log_types = gpgpusim_case()
+        write_gpgpusim_log(os.path.join(ds, "trace_set.log"), log_blocks, log_types, truncate_last=5)
+        outdir = os.path.join(tmp, "out_log")
+        os.makedirs(outdir)
+        r = subprocess.run([REF_BIN, "-a", "VPC", "-i", os.path.join(ds, "trace_set.log"), "-c", os.path.join(ROOT, "configs", "P6.json"),
+                            "-o", outdir], capture_output=True, text=True, check=True)
+        with open(os.path.join(outdir, "P6_results.csv")) as f, open(os.path.join(gold, "cli_log_P6_results.csv"), "w") as g:
+            g.write(f.read())
+        with open(os.path.join(outdir, "P6_results_detail.csv")) as f, open(os.path.join(gold, "cli_log_P6_results_detail.csv"), "w") as g:
+            g.write(f.read())
+        view = subprocess.run([REF_BIN, "-a", "VIEWER", "-i", os.path.join(ds, "trace_set.log")], capture_output=True, text=True, check=True).stdout
+        view_npy = subprocess.run([REF_BIN, "-a", "VIEWER", "-i", os.path.join(ds, "golden_set.npy")], capture_output=True, text=True, check=True).stdout
+        sc2 = subprocess.run([REF_BIN, "-a", "BDI", "-i", os.path.join(ds, "trace_set.log"), "-o", outdir], capture_output=True, text=True, check=True)
+        with open(os.path.join(outdir, "BDI_results.csv")) as f:
+            bdi_csv = f.read()
+        with open(os.path.join(gold, "cli_log.json"), "w") as g:
+            json.dump({"vpc_stdout": r.stdout, "viewer_sha256": hashlib.sha256(view.encode()).hexdigest(), "viewer_lines": view.count("\n"),
+                       "viewer_head": view.splitlines()[:3], "viewer_npy_sha256": hashlib.sha256(view_npy.encode()).hexdigest(),
+                       "viewer_npy_lines": view_npy.count("\n"), "bdi_stdout": sc2.stdout, "bdi_csv": bdi_csv}, g, indent=1)
+        print("log cli:", r.stdout.strip(), "viewer lines", view.count("\n"), "bdi", sc2.stdout.strip())
         # secondary variants (config #5) through the reference CLI, on a 12 001-row dump so that SC2 leaves its
         # 10 000-line sampling phase (main.cpp:108-114); the dump is synth("mixed_hashed", 555, 0, 12000, 12000) + 1 row
         np.save(os.path.join(ds, "variants_set.npy"),

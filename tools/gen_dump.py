@@ -113,6 +113,32 @@ def kat_blocks():
     return b
 
 
+GPGPUSIM_KEYS = [("kid", 1), ("mftype", 1), ("cycle", 8), ("tpc", 4), ("sid", 4), ("wid", 4), ("pc", 4), ("instcn", 4),
+                 ("addr", 8), ("reqtyp", 4), ("row", 4), ("chip", 4), ("bank", 4), ("col", 4), ("reqsiz", 4), ("data", 0),
+                 ("pad", 0)]
+
+
+def write_gpgpusim_log(path, blocks, req_types, truncate_last=0):
+    """Binary GPGPU-Sim trace as the reference's gpgpusim::LoaderGPGPU reads it (LoaderGPGPU.cpp:26-54, 82-113):
+    1 byte key count (17), 17 x (6-char key, 1-byte size), then per record 62 header bytes + req_size payload bytes.
+    req_types[i] is the record's request type (0 = GLOBAL_ACC_R and 4 = GLOBAL_ACC_W are the ones the driver keeps,
+    main.cpp:222-224).  truncate_last > 0 cuts that many bytes off the end (an incomplete last record)."""
+    import struct
+    out = bytearray()
+    out += bytes([len(GPGPUSIM_KEYS)])
+    for name, size in GPGPUSIM_KEYS:
+        out += name.encode().ljust(6, b"\0")[:6] + bytes([size])
+    for i, (blk, rt) in enumerate(zip(blocks, req_types)):
+        payload = bytes(blk)
+        out += struct.pack("<BBQIIIIIQIIIIII", i % 3, 0 if rt < 4 else 1, 1000 + 7 * i, i % 8, i % 16, i % 48, 0x100 + 8 * i, i,
+                           0x7F0000000000 + 128 * i, int(rt), i % 1024, i % 4, i % 16, i % 64, len(payload))
+        out += payload
+    if truncate_last:
+        out = out[:-truncate_last]
+    with open(path, "wb") as f:
+        f.write(out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("out")
