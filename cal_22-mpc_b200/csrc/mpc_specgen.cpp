@@ -666,7 +666,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   out.push_back(fmt("  static constexpr int kFirst = %d;", first));
   out.push_back(fmt("  static constexpr bool kHasWordSame = %s;", cfg.has_wordsame ? "true" : "false"));
   // register budget: plane-major modules keep the line, its residues and the transposed rows live at once;
-  // column-major only: 16 warps in ONE CTA per SM (<= 128 registers) so that the 64 KiB row-cost table, the 128 KiB of
+  // column-major only: 20 warps in ONE CTA per SM (96 registers), one 4 KiB tile stage per warp, so that the 64 KiB row-cost table, the
   // tile stages and the histogram fit the 227 KiB of shared memory
   out.push_back(fmt("  static constexpr int kWarps = %d;", t.warps));
   out.push_back(fmt("  static constexpr int kStages = %d;  // shared-memory tile stages per warp", t.stages));
