@@ -33,12 +33,31 @@ MPC_HD int popc64(uint64_t v) {
 
 // ---- BDI ------------------------------------------------------------------------------------------------------
 // BDI::reduceSign, BDI.cpp:203-218: a negative value keeps (index of its highest zero bit + 2) low bits; all ones
-// comes back unchanged (and therefore never fits a delta).
+// comes back unchanged (and therefore never fits a delta).  Kept as the written-down rule; the kernels use the
+// closed form below.
 MPC_HD uint64_t bdi_reduce_sign(uint64_t x) {
   if ((x >> 63) == 0 || x == ~0ull) return x;
   const int hz = 63 - clz64(~x);  // highest zero bit, 0..62
   const int keep = hz + 2;        // 2..64
   return keep >= 64 ? x : (x & ((1ull << keep) - 1ull));
+}
+
+// reduceSign(x) <= 2^(8D) - 1 in closed form.  For x = -k < 0 the kept value is 2^keep - k with
+// 2^(keep-1) <= 2^keep - k < 2^keep and keep = (bit length of k-1) + 1, so it fits exactly when keep <= 8D, i.e.
+// 2 <= k <= 2^(8D-1) (k = 1, all ones, never fits); x >= 0 fits when x < 2^(8D).  As one range test on x + 2^(8D-1):
+// x in [-2^(8D-1), 2^(8D)) and x != -1.  tests/test_swar_host.py checks it against bdi_reduce_sign on the boundaries.
+template <int D>
+MPC_HD bool bdi_fits64(uint64_t x) {
+  constexpr uint64_t half = 1ull << (8 * D - 1);
+  return (x + half) < 3ull * half && x != ~0ull;
+}
+// the same test for base - v with both < 2^32 (base sizes 4 and 2), in 32-bit arithmetic: the 64-bit difference is
+// d (v <= base) or d - 2^32 (v > base) with d = (base - v) mod 2^32
+template <int D>
+MPC_HD bool bdi_delta_fits32(uint32_t base, uint32_t v) {
+  constexpr uint32_t half = 1u << (8 * D - 1);
+  const uint32_t d = base - v;
+  return v <= base ? d <= 2u * half - 1u : (d + half) <= half - 2u;
 }
 
 template <int B>
@@ -48,24 +67,46 @@ MPC_HD uint64_t bdi_value(const uint32_t (&x)[32], int i) {  // little-endian ch
   return (x[i >> 1] >> (16 * (i & 1))) & 0xffffu;
 }
 
-// BDI::checkBDI, BDI.cpp:108-201
+// BDI::checkBDI, BDI.cpp:108-201: immediates (values that fit D bytes on their own), the first other value is the
+// base, every later one must be within a D-byte delta of it.
 template <int B, int D>
 MPC_HD uint32_t bdi_check(const uint32_t (&x)[32]) {
   constexpr int n = 128 / B;
-  constexpr uint64_t limit = D == 1 ? 0xffull : D == 2 ? 0xffffull : 0xffffffffull;
-  uint64_t imm_mask = 0;
+  uint32_t imm = 0;
+  bool not_all = false;
+  if (B == 8) {
+    // base = first non-immediate value: select chain from the back
+    uint64_t base = 0;
+    uint32_t imm_mask = 0;
 #pragma unroll
-  for (int i = 0; i < n; i++)
-    if (bdi_reduce_sign(bdi_value<B>(x, i)) <= limit) imm_mask |= 1ull << i;
-  const uint32_t imm = (uint32_t)popc64(imm_mask);
-  bool have_base = false, not_all = false;
-  uint64_t base = 0;
+    for (int i = n - 1; i >= 0; i--) {
+      const uint64_t v = bdi_value<8>(x, i);
+      const bool im = bdi_fits64<D>(v);
+      imm_mask |= (im ? 1u : 0u) << i;
+      base = im ? base : v;
+    }
+    imm = (uint32_t)popc32(imm_mask);
 #pragma unroll
-  for (int i = 0; i < n; i++) {
-    if ((imm_mask >> i) & 1ull) continue;
-    const uint64_t v = bdi_value<B>(x, i);
-    if (!have_base) { base = v; have_base = true; }
-    else if (bdi_reduce_sign(base - v) > limit) not_all = true;
+    for (int i = 0; i < n; i++) {
+      const uint64_t v = bdi_value<8>(x, i);
+      // immediates are skipped; the base itself passes (difference 0)
+      not_all |= !((imm_mask >> i) & 1u) && !bdi_fits64<D>(base - v);
+    }
+  } else {
+    constexpr uint32_t limit = D == 1 ? 0xffu : 0xffffu;  // zero-extended values are never negative
+    uint32_t base = 0;
+#pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+      const uint32_t v = (uint32_t)bdi_value<B>(x, i);
+      const bool im = v <= limit;
+      imm += im ? 1u : 0u;
+      base = im ? base : v;
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      const uint32_t v = (uint32_t)bdi_value<B>(x, i);
+      not_all |= v > limit && !bdi_delta_fits32<D>(base, v);
+    }
   }
   if (not_all) return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)n - imm) * (uint32_t)B);
   return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)B + ((uint32_t)n - imm - 1u) * (uint32_t)D));  // wraps when imm == n
@@ -81,13 +122,16 @@ MPC_HD uint32_t bdi_block(const uint32_t (&x)[32], int* state) {
   if (any == 0) { best = 8; sel = 0; }
   else if (rep == 0) { best = 64; sel = 1; }
   else {
+    // A check either fits -- then its size is the constant n + 8 (B - D + n D) whatever the number of immediates -- or
+    // costs more than that, and a later check only replaces an earlier one when strictly smaller (BDI.cpp:30-66): a
+    // check whose fitting size cannot beat the best so far is skipped.
     uint32_t cur;
-    cur = bdi_check<8, 1>(x); if (best > cur) { best = cur; sel = 2; }
-    cur = bdi_check<8, 2>(x); if (best > cur) { best = cur; sel = 3; }
-    cur = bdi_check<8, 4>(x); if (best > cur) { best = cur; sel = 4; }
-    cur = bdi_check<4, 1>(x); if (best > cur) { best = cur; sel = 5; }
-    cur = bdi_check<4, 2>(x); if (best > cur) { best = cur; sel = 6; }
-    cur = bdi_check<2, 1>(x); if (best > cur) { best = cur; sel = 7; }
+    cur = bdi_check<8, 1>(x); if (best > cur) { best = cur; sel = 2; }                       // fits: 200
+    if (best > 320u) { cur = bdi_check<8, 2>(x); if (best > cur) { best = cur; sel = 3; } }  // fits: 320
+    if (best > 560u) { cur = bdi_check<8, 4>(x); if (best > cur) { best = cur; sel = 4; } }  // fits: 560
+    if (best > 312u) { cur = bdi_check<4, 1>(x); if (best > cur) { best = cur; sel = 5; } }  // fits: 312
+    if (best > 560u) { cur = bdi_check<4, 2>(x); if (best > cur) { best = cur; sel = 6; } }  // fits: 560
+    if (best > 584u) { cur = bdi_check<2, 1>(x); if (best > cur) { best = cur; sel = 7; } }  // fits: 584
     if (best == 1024u) sel = 8;
   }
   *state = sel;

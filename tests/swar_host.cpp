@@ -43,3 +43,15 @@ extern "C" void t_variant_run(int alg, const unsigned char* lines, unsigned long
     }
   }
 }
+
+// BDI closed-form range tests vs the written-down reduceSign rule (BDI.cpp:203-218)
+extern "C" int t_bdi_fits(unsigned long long x, int D) {
+  return D == 1 ? mpcvar::bdi_fits64<1>(x) : D == 2 ? mpcvar::bdi_fits64<2>(x) : mpcvar::bdi_fits64<4>(x);
+}
+extern "C" int t_bdi_fits_rule(unsigned long long x, int D) {
+  const unsigned long long limit = D == 1 ? 0xffull : D == 2 ? 0xffffull : 0xffffffffull;
+  return mpcvar::bdi_reduce_sign(x) <= limit;
+}
+extern "C" int t_bdi_delta32(unsigned base, unsigned v, int D) {
+  return D == 1 ? mpcvar::bdi_delta_fits32<1>(base, v) : mpcvar::bdi_delta_fits32<2>(base, v);
+}

@@ -107,3 +107,65 @@ def test_variant_block_functions_match_oracle(swar, alg):
     bad = np.nonzero(sizes != want_sizes)[0]
     assert bad.size == 0, (bad[:5], sizes[bad[:5]], want_sizes[bad[:5]])
     assert np.array_equal(counts, want_counts)
+
+
+def test_bdi_range_tests_equal_the_reduce_sign_rule(swar):
+    """bdi_fits64 / bdi_delta_fits32 (closed form) against reduceSign (BDI.cpp:203-218) on every boundary."""
+    swar.t_bdi_fits.argtypes = swar.t_bdi_fits_rule.argtypes = [ctypes.c_ulonglong, ctypes.c_int]
+    swar.t_bdi_delta32.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_int]
+    M = (1 << 64) - 1
+    rng = np.random.default_rng(11)
+    for D in (1, 2, 4):
+        half, full = 1 << (8 * D - 1), 1 << (8 * D)
+        pts = {0, 1, half - 1, half, half + 1, full - 2, full - 1, full, full + 1, 1 << 62, (1 << 63) - 1, 1 << 63, (1 << 63) + 1}
+        for k in (1, 2, 3, half - 1, half, half + 1, full - 1, full, full + 1, 1 << 40, 1 << 62):
+            pts.add((-k) & M)
+        for bits in range(1, 64):
+            for dlt in (-1, 0, 1):
+                pts.add(((1 << bits) + dlt) & M)
+                pts.add((-(1 << bits) + dlt) & M)
+        pts.update(int(v) for v in rng.integers(0, 1 << 63, 2000, dtype=np.uint64) * 2 + rng.integers(0, 2, 2000, dtype=np.uint64))
+        for x in pts:
+            assert swar.t_bdi_fits(x, D) == swar.t_bdi_fits_rule(x, D), (hex(x), D)
+    for D in (1, 2):
+        half, full = 1 << (8 * D - 1), 1 << (8 * D)
+        bases = [0, 1, 5, half, full - 1, full, 0x7fffffff, 0x80000000, 0xffffffff - 3, 0xffffffff] + [int(v) for v in rng.integers(0, 1 << 32, 60)]
+        for base in bases:
+            for off in (0, 1, 2, 3, half - 1, half, half + 1, full - 1, full, full + 1, 0x7fffffff, 0x80000000, 0xfffffff0):
+                for v in {(base + off) & 0xffffffff, (base - off) & 0xffffffff, off, 0xffffffff - off}:
+                    assert swar.t_bdi_delta32(base, v, D) == swar.t_bdi_fits_rule((base - v) & M, D), (base, v, D)
+
+
+def test_bdi_blocks_on_delta_boundaries_match_oracle(swar):
+    """Blocks whose values sit on the immediate / delta limits of every (base size, delta size) pair."""
+    from oracle.bridge import oracle_variant
+    import random
+    rnd = random.Random(12)
+    blocks = []
+    for B, dt in ((8, np.uint64), (4, np.uint32), (2, np.uint16)):
+        n = 128 // B
+        top = (1 << (8 * B)) - 1
+        for D in (1, 2, 4):
+            if D >= B:
+                continue
+            half, full = 1 << (8 * D - 1), 1 << (8 * D)
+            for base in (full, full + 7, top - full, top, top - 1, (top >> 1) + 1, rnd.randrange(full, top)):
+                for offs in ([0, -1, -2], [1, 2, half - 1, half, half + 1], [-half + 1, -half, -half - 1], [full - 1, full, -full],
+                             [0] * 3, [-1] * 3, [half] * 3):
+                    vals = np.full(n, base, dtype=object)
+                    for j, o in enumerate(offs):
+                        vals[1 + 3 * j % (n - 1)] = (base - o) & top
+                    vals[n - 1] = rnd.randrange(0, full)  # an immediate
+                    blocks.append(np.array([int(v) for v in vals], dtype=dt).view(np.uint8))
+                    vals[0] = rnd.randrange(0, full)  # immediate first: the base is the second value
+                    blocks.append(np.array([int(v) for v in vals], dtype=dt).view(np.uint8))
+    d = np.stack(blocks)
+    want_sizes, want_counts = oracle_variant("BDI", d)
+    sizes = np.zeros(d.shape[0], np.uint32)
+    counts = np.zeros(16, np.uint64)
+    swar.t_variant_run.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+    swar.t_variant_run(1, d.ctypes.data, d.shape[0], sizes.ctypes.data, counts.ctypes.data)
+    bad = np.nonzero(sizes != want_sizes)[0]
+    assert bad.size == 0, (bad[:5], sizes[bad[:5]], want_sizes[bad[:5]])
+    assert np.array_equal(counts, want_counts)
+    assert len(set(sizes.tolist())) > 8  # the set really exercises several encodings
