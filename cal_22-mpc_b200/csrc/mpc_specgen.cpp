@@ -607,10 +607,11 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   // column-major only: ONE CTA of 20 warps per SM at 96 registers (the next allocation step down, 80, spills), one
   // 4 KiB tile stage per warp; measured on B200: 16 warps x 2 stages 4.11 TB/s, 18 x 1 4.16, 20 x 1 4.26, 21/22/24 x 1 (80
   // registers) 3.86-3.93 on the headline workload
-  t.warps = (t.use_lut && !has_pm) ? 20 : 8;
-  t.stages = (t.use_lut && !has_pm) ? 1 : 2;
-  t.min_ctas = has_pm ? 1 : 2;
-  if (t.warps >= 16) t.min_ctas = 1;
+  t.warps = (t.use_lut && !has_pm) ? 20 : 16;
+  // configs with plane-major modules: ONE CTA of 16 warps at 128 registers (measured against 8 warps at 160 registers, the
+  // former choice: P6 smooth 1.42 -> 1.79 TB/s, random 2.23 -> 2.72, E5 mixed 2.08 -> 2.82; 20 warps at 96 registers spill)
+  t.stages = 1;
+  t.min_ctas = 1;
   if ((e = getenv("MPC_SPEC_WARPS")) && atoi(e) > 0) { t.warps = atoi(e); t.min_ctas = t.warps >= 16 ? 1 : t.min_ctas; }  // tuning overrides
   if ((e = getenv("MPC_SPEC_MIN_CTAS")) && atoi(e) > 0) t.min_ctas = atoi(e);
   e = getenv("MPC_SPEC_SKIP");
