@@ -33,6 +33,7 @@ struct Driver {
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;  // optional: programmatic dependent launch
   bool ok = false;
 };
 
@@ -53,6 +54,7 @@ Driver& driver() {
            entry("cuModuleGetFunction", &d.ModuleGetFunction) && entry("cuFuncSetAttribute", &d.FuncSetAttribute) &&
            entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", &d.OccupancyMaxActiveBlocksPerMultiprocessor) &&
            entry("cuLaunchKernel", &d.LaunchKernel);
+    entry("cuLaunchKernelEx", &d.LaunchKernelEx);
   });
   return d;
 }
@@ -164,8 +166,27 @@ cudaError_t jit_launch(JitKernel* k, const uint8_t* d_lines, uint64_t n_blocks, 
   unsigned int static_rounds = eighths == 8 ? (unsigned int)((n_tiles + total_warps - 1) / total_warps)
                                             : (unsigned int)((n_tiles / total_warps) * (uint64_t)eighths / 8);
   void* args[] = {(void*)&d_lines, (void*)&n, (void*)&d_packed, (void*)&d_stats, (void*)&d_row_lut, (void*)&d_sched, (void*)&static_rounds};
-  CUresult r = driver().LaunchKernel(k->fn, (unsigned)grid, 1, 1, (unsigned)(k->traits.warps * 32), 1, 1,
-                                     (unsigned)k->traits.smem_bytes, (CUstream)stream, args, nullptr);
+  CUresult r;
+  const char* pdl = getenv("MPC_PDL");
+  if (driver().LaunchKernelEx && !(pdl && pdl[0] == '0')) {
+    // same launch attribute as launch_spec (mpc_spec.cuh): the prologue may overlap the previous kernel's tail
+    CUlaunchConfig lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDimX = (unsigned)grid; lc.gridDimY = 1; lc.gridDimZ = 1;
+    lc.blockDimX = (unsigned)(k->traits.warps * 32); lc.blockDimY = 1; lc.blockDimZ = 1;
+    lc.sharedMemBytes = (unsigned)k->traits.smem_bytes;
+    lc.hStream = (CUstream)stream;
+    CUlaunchAttribute attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    attr.value.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = &attr;
+    lc.numAttrs = 1;
+    r = driver().LaunchKernelEx(&lc, k->fn, args, nullptr);
+  } else {
+    r = driver().LaunchKernel(k->fn, (unsigned)grid, 1, 1, (unsigned)(k->traits.warps * 32), 1, 1,
+                              (unsigned)k->traits.smem_bytes, (CUstream)stream, args, nullptr);
+  }
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
 }
 

@@ -103,6 +103,32 @@ def test_statistics_accumulate_and_reset(mpcb):
     assert m.finish().blocks == 0
 
 
+@pytest.mark.parametrize("cfg", ["F4", "P6"])
+def test_back_to_back_launches_of_any_size_share_one_tile_counter(mpcb, cfg):
+    """The specialised kernel hands out its last tiles through an atomic counter that the last CTA of a launch puts back to
+    zero: launches of very different sizes, back to back on one stream without a reset in between, must each see every
+    block exactly once (per-block results) and add up in the statistics."""
+    import torch
+    m = mpcb.Mpc(cfg_path(cfg))
+    sizes_n = [1, 5000, 33, 148 * 20 * 32 * 9 + 17, 7, 300000, 64, 148 * 20 * 32 + 1]
+    total = sum(sizes_n)
+    blocks = synth("mixed_hashed", 21, 0, total, total)
+    d = torch.from_numpy(blocks).cuda()
+    packed = torch.zeros(total, dtype=torch.int16, device="cuda")
+    m.reset()
+    off = 0
+    for rep in range(2):  # second round: the same launches again, the counter has been through every size already
+        off = 0
+        for n in sizes_n:
+            m.submit_device(d.data_ptr() + off * 128, n, packed.data_ptr() + off * 2)
+            off += n
+    st = m.finish()
+    r = OracleMPC(cfg_path(cfg)).run(blocks)
+    got_sizes, got_sels = mpcb.unpack(packed.cpu().numpy().view(np.uint16))
+    assert np.array_equal(got_sizes, r.sizes) and np.array_equal(got_sels, r.sels)
+    assert st.blocks == 2 * total and st.CompressedSize == 2 * r.CompressedSize and np.array_equal(st.count, 2 * r.count)
+
+
 def test_device_submit_and_synth_match_numpy(mpcb):
     import torch
     m = mpcb.Mpc(cfg_path("P6"))
