@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <unistd.h>
 #include <thread>
 
 namespace comp {
@@ -156,7 +157,16 @@ CompResult* VPC::GetResult() {
     std::vector<ncclComm_t> comms(G);
     std::vector<int> devs(G);
     for (int g = 0; g < G; g++) devs[g] = g;
-    if (ncclCommInitAll(comms.data(), G, devs.data()) != ncclSuccess) { printf("ncclCommInitAll failed\n"); exit(1); }
+    // stdout carries exactly what the reference prints ("comp.ratio: ..."): whatever NCCL writes while it initialises (its
+    // version line under NCCL_DEBUG=VERSION, which this image sets, goes to stdout) is sent to stderr instead
+    fflush(stdout);
+    const int saved_stdout = dup(1);
+    dup2(2, 1);
+    const ncclResult_t init_rc = ncclCommInitAll(comms.data(), G, devs.data());
+    fflush(stdout);
+    dup2(saved_stdout, 1);
+    close(saved_stdout);
+    if (init_rc != ncclSuccess) { printf("ncclCommInitAll failed\n"); exit(1); }
     for (int g = 0; g < G; g++) mpc_sync(m_Ctx[g]);
     ncclGroupStart();
     for (int g = 0; g < G; g++) {

@@ -132,3 +132,27 @@ def test_variant_csv_bytes_equal_reference(tmp_path, alg):
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout == open(os.path.join(GOLD, f"cli_{alg}_stdout.txt")).read()
     assert open(out / f"{alg}_results.csv").read() == open(os.path.join(GOLD, f"cli_{alg}_results.csv")).read()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_cli_equals_reference(tmp_path, golden):
+    """--gpus 2: contiguous shards on two devices, statistics all-reduced with NCCL; the CSV bytes must
+    still be the reference's.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _build()
+    ds = tmp_path / "ds"
+    out = tmp_path / "out"
+    ds.mkdir()
+    out.mkdir()
+    np.save(ds / "golden_set.npy", np.concatenate([golden["blocks"][:199], np.zeros((1, 128), np.uint8)]))
+    stdout = ""
+    for _ in range(2):
+        r = subprocess.run([BIN, "-a", "VPC", "-i", str(ds / "golden_set.npy"), "-c", cfg_path("F4"), "-o", str(out), "--gpus", "2"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        stdout = r.stdout
+    assert stdout == open(os.path.join(GOLD, "cli_F4_stdout.txt")).read()
+    for suffix in ("results.csv", "results_detail.csv"):
+        assert open(out / f"F4_{suffix}").read() == open(os.path.join(GOLD, f"cli_F4_{suffix}")).read(), suffix
