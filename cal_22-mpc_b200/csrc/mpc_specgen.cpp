@@ -439,105 +439,35 @@ void emit_score_cm(const Module& m, Lines& out) {
   for (int k = 0; k < 64; k++)
     for (int cidx : {cols[2 * k], cols[2 * k + 1]})
       if (cidx >= 0) tests[k][cidx / 4] |= 0xFFu << (8 * (cidx % 4));
-  // rows without a column (short scan tables) are zero rows: they never end the count
-  std::vector<int> rows;
-  for (int k = 0; k < 64; k++)
-    if (!tests[k].empty()) rows.push_back(k);
-  auto define_words = [&](const std::vector<int>& rs, const char* indent) {
-    for (int kk : rs)
+  for (int k = 0; k < 64; k += 2) {
+    std::vector<int> group;
+    for (int kk : {k, k + 1})
+      if (kk < 64 && !tests[kk].empty()) group.push_back(kk);
+    for (int kk : group)
       for (auto& wm : tests[kk])
         if (!have.count(wm.first)) {
-          out.push_back(fmt("%sconst uint32_t e%d = %s;", indent, wm.first, m.eq_expr(wm.first).c_str()));
+          out.push_back(fmt("  const uint32_t e%d = %s;", wm.first, m.eq_expr(wm.first).c_str()));
           have.insert(wm.first);
         }
-  };
-  auto row_expr = [&](int kk) {
-    std::vector<std::pair<uint32_t, std::vector<std::string>>> terms;  // grouped by mask, first-appearance order
-    for (auto& wm : tests[kk]) {
-      auto it = std::find_if(terms.begin(), terms.end(), [&](auto& t) { return t.first == wm.second; });
-      if (it == terms.end()) { terms.push_back({wm.second, {}}); it = terms.end() - 1; }
-      it->second.push_back(fmt("e%d", wm.first));
-    }
-    std::vector<std::string> parts;
-    for (auto& t : terms)
-      parts.push_back(t.first != 0xFFFFFFFFu ? fmt("((%s) & 0x%08xu)", join(t.second, " | ").c_str(), t.first)
-                                              : fmt("(%s)", join(t.second, " | ").c_str()));
-    return join(parts, " | ");
-  };
-  // row-by-row walk, two rows per branch; the words a test needs are defined right before it
-  auto emit_fine = [&](const std::vector<int>& rs, const char* indent, bool lazy_words) {
-    for (size_t i = 0; i < rs.size(); i += 2) {
-      std::vector<int> group(rs.begin() + i, rs.begin() + std::min(i + 2, rs.size()));
-      if (lazy_words) define_words(group, indent);
-      if (group.size() == 2)
-        out.push_back(fmt("%s{ const uint32_t t0 = %s, t1 = %s; if ((t0 | t1) != 0u) return t0 ? %du : %du; }", indent, row_expr(group[0]).c_str(),
-                          row_expr(group[1]).c_str(), group[0], group[1]));
-      else
-        out.push_back(fmt("%sif ((%s) != 0u) return %du;", indent, row_expr(group[0]).c_str(), group[0]));
-    }
-  };
-  // Segments after the first two rows: a RUN is a stretch of >= 4 consecutive rows that all test the same byte lane(s) of
-  // ordinary line words (not word 0, whose root byte is special); with G = OR of every e-word, (G & lanes) == 0 proves the
-  // whole run zero in two instructions, otherwise the run is walked row by row.  Everything else is walked row by row.
-  struct Seg { bool run; uint32_t mask; std::vector<int> rows; };
-  std::vector<Seg> segs;
-  auto simple_mask = [&](int kk) -> uint32_t {  // 0 when the row is not a candidate for a run
-    uint32_t mk = 0;
-    for (auto& wm : tests[kk]) {
-      if (wm.first == 0) return 0u;
-      if (mk == 0) mk = wm.second;
-      else if (mk != wm.second) return 0u;
-    }
-    return mk;
-  };
-  const size_t first = std::min<size_t>(2, rows.size());
-  for (size_t i = first; i < rows.size();) {
-    const uint32_t mk = simple_mask(rows[i]);
-    size_t j = i + 1;
-    if (mk)
-      while (j < rows.size() && simple_mask(rows[j]) == mk) j++;
-    const bool run = mk != 0 && j - i >= 4;
-    if (!run) j = i + 1;
-    std::vector<int> rs(rows.begin() + i, rows.begin() + j);
-    if (!run && !segs.empty() && !segs.back().run) segs.back().rows.insert(segs.back().rows.end(), rs.begin(), rs.end());
-    else segs.push_back({run, mk, rs});
-    i = j;
-  }
-  bool any_run = false;
-  for (auto& sg : segs) any_run |= sg.run;
-  const char* env = getenv("MPC_SPEC_COARSE");
-  if (env && env[0] == '0') any_run = false;
-  if (!any_run) {
-    emit_fine(rows, "  ", true);
-  } else {
-    emit_fine(std::vector<int>(rows.begin(), rows.begin() + first), "  ", true);  // most losing predictors stop here
-    std::set<int> gwords;
-    for (auto& sg : segs) {
-      define_words(sg.rows, "  ");
-      if (sg.run)
-        for (int kk : sg.rows)
-          for (auto& wm : tests[kk]) gwords.insert(wm.first);
-    }
-    std::vector<std::string> terms;
-    for (int w : gwords) terms.push_back(fmt("e%d", w));
-    while (terms.size() > 1) {  // three-input ORs
-      std::vector<std::string> next;
-      for (size_t i = 0; i < terms.size(); i += 3) {
-        std::vector<std::string> grp(terms.begin() + i, terms.begin() + std::min(i + 3, terms.size()));
-        next.push_back(grp.size() == 1 ? grp[0] : "(" + join(grp, " | ") + ")");
+    std::vector<std::pair<int, std::string>> exprs;
+    for (int kk : group) {
+      std::vector<std::pair<uint32_t, std::vector<std::string>>> terms;  // grouped by mask, first-appearance order
+      for (auto& wm : tests[kk]) {
+        auto it = std::find_if(terms.begin(), terms.end(), [&](auto& t) { return t.first == wm.second; });
+        if (it == terms.end()) { terms.push_back({wm.second, {}}); it = terms.end() - 1; }
+        it->second.push_back(fmt("e%d", wm.first));
       }
-      terms.swap(next);
+      std::vector<std::string> parts;
+      for (auto& t : terms)
+        parts.push_back(t.first != 0xFFFFFFFFu ? fmt("((%s) & 0x%08xu)", join(t.second, " | ").c_str(), t.first)
+                                                : fmt("(%s)", join(t.second, " | ").c_str()));
+      exprs.push_back({kk, join(parts, " | ")});
     }
-    out.push_back(fmt("  const uint32_t G = %s;  // OR of the e-words of the runs below: a zero byte lane = that byte is zero in all of them", terms[0].c_str()));
-    for (auto& sg : segs) {
-      if (sg.run) {
-        out.push_back(fmt("  if ((G & 0x%08xu) != 0u) {  // rows %d..%d", sg.mask, sg.rows.front(), sg.rows.back()));
-        emit_fine(sg.rows, "    ", false);
-        out.push_back("  }");
-      } else {
-        emit_fine(sg.rows, "  ", false);
-      }
-    }
+    if (exprs.size() == 2)
+      out.push_back(fmt("  { const uint32_t t0 = %s, t1 = %s; if ((t0 | t1) != 0u) return t0 ? %du : %du; }", exprs[0].second.c_str(),
+                        exprs[1].second.c_str(), exprs[0].first, exprs[1].first));
+    else if (exprs.size() == 1)
+      out.push_back(fmt("  if ((%s) != 0u) return %du;", exprs[0].second.c_str(), exprs[0].first));
   }
   out.push_back("  return 64u;");
   out.push_back("}");
