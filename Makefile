@@ -12,7 +12,7 @@ CXXFLAGS := -O3 -std=c++17 -fPIC -Iinclude -I$(CSRC) -Wall
 LIB      := $(PKG)/libmpc_b200.so
 SPEC_CFGS := P6 F4 Z1 E5
 SPEC_SRCS := $(foreach c,$(SPEC_CFGS),$(CSRC)/spec/spec_$(c).cu)
-CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_variants.cu $(CSRC)/mpc_sc2.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu $(SPEC_SRCS)
+CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_variants.cu $(CSRC)/mpc_sc2.cu $(CSRC)/mpc_pattern.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu $(SPEC_SRCS)
 CU_OBJS  := $(CU_SRCS:.cu=.o)
 CC_OBJS  := $(CSRC)/mpc_config.o $(CSRC)/mpc_specgen.o $(CSRC)/mpc_jit.o
 

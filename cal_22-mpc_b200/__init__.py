@@ -7,9 +7,9 @@ used by the tests and bench.py.  Import with importlib (the directory name has a
     mpcb = importlib.import_module("cal_22-mpc_b200")
 """
 from .capi import (ConfigPod, ModulePod, Mpc, MpcError, Stats, StatsPod, SYN, LIB_PATH, SYMBOLS, lib, load_config,
-                   unpack, variant_run, VariantStats, sc2_run, sc2_sampling_lines, cpack_run, jit_compile_check)
+                   unpack, variant_run, VariantStats, sc2_run, sc2_sampling_lines, cpack_run, jit_compile_check, pattern_run, PatternStats)
 
 from .shard import allreduce_stats, shard_range
 
 __all__ = ["allreduce_stats", "shard_range", "ConfigPod", "ModulePod", "Mpc", "MpcError", "Stats", "StatsPod", "SYN", "LIB_PATH", "SYMBOLS", "lib",
-           "load_config", "unpack", "variant_run", "VariantStats", "sc2_run", "sc2_sampling_lines", "cpack_run", "jit_compile_check"]
+           "load_config", "unpack", "variant_run", "VariantStats", "sc2_run", "sc2_sampling_lines", "cpack_run", "jit_compile_check", "pattern_run", "PatternStats"]

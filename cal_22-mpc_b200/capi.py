@@ -39,6 +39,21 @@ class StatsPod(C.Structure):
                 ("hist", (C.c_uint64 * HIST_BINS) * (MAX_MODULES + 1))]
 
 
+class PatternStats(C.Structure):
+    """mpc_pattern_stats (include/mpc_capi.h)"""
+    _fields_ = [("blocks", C.c_uint64), ("total_bytes", C.c_uint64), ("zeros_bytes", C.c_uint64),
+                ("repeated_bytes", C.c_uint64), ("temporal_bytes", C.c_uint64), ("undefined_bytes", C.c_uint64),
+                ("implicit_bytes", C.c_uint64 * 6), ("explicit_bytes", C.c_uint64 * 6),
+                ("symbol_counts", C.c_uint64 * 256), ("symbol_counts_nontrivial", C.c_uint64 * 256),
+                ("distinct_blocks", C.c_uint64), ("temporal_path", C.c_int32)]
+
+    def words(self):
+        """the counters in the layout of the CPU oracle (orc_pattern_run)"""
+        return np.array([self.zeros_bytes, self.repeated_bytes, self.temporal_bytes, self.undefined_bytes, self.total_bytes]
+                        + list(self.implicit_bytes) + list(self.explicit_bytes) + list(self.symbol_counts)
+                        + list(self.symbol_counts_nontrivial), dtype=np.uint64)
+
+
 class VariantStats(C.Structure):
     _fields_ = [("blocks", C.c_uint64), ("original_bits", C.c_uint64), ("compressed_bits", C.c_uint64),
                 ("counts", C.c_uint64 * 16)]
@@ -61,7 +76,8 @@ SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config
            "mpc_submit_device", "mpc_submit_host", "mpc_sync", "mpc_stats_device_ptr", "mpc_finish",
            "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version",
            "mpc_variant_run_device", "mpc_variant_run_host", "mpc_variant_error", "mpc_sc2_run_device", "mpc_sc2_run_host",
-           "mpc_sc2_error", "mpc_cpack_run_host", "mpc_jit_compile_check", "mpc_enable_timing"]
+           "mpc_sc2_error", "mpc_cpack_run_host", "mpc_jit_compile_check", "mpc_enable_timing",
+           "mpc_pattern_run_device", "mpc_pattern_run_host", "mpc_pattern_error"]
 
 
 def lib():
@@ -104,6 +120,9 @@ def lib():
     l.mpc_sc2_run_host.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
     l.mpc_sc2_error.restype = C.c_char_p
     l.mpc_cpack_run_host.argtypes = [vp, u64, C.c_uint32, vp, C.POINTER(VariantStats)]
+    l.mpc_pattern_run_device.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(PatternStats), C.POINTER(C.c_float)]
+    l.mpc_pattern_run_host.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(PatternStats), C.POINTER(C.c_float)]
+    l.mpc_pattern_error.restype = C.c_char_p
     _LIB = l
     return l
 
@@ -291,6 +310,23 @@ def cpack_run(lines, line_size=128):
     if rc != 0:
         raise MpcError(f"CPACK failed ({rc})")
     return sizes, st
+
+
+def pattern_run(lines=None, device_ptr=None, n_blocks=None, cache_blocks=0, device=0, want_sizes=True, line_size=128):
+    """PATTERN analysis over host blocks (numpy) or a device pointer -> (sizes or None, PatternStats, device_ms)."""
+    st, ms = PatternStats(), C.c_float()
+    if device_ptr is None:
+        lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, line_size)
+        n = lines.shape[0]
+        sizes = np.zeros(n, dtype=np.uint16) if want_sizes else None
+        rc = lib().mpc_pattern_run_host(device, lines.ctypes.data, n, line_size, cache_blocks,
+                                        sizes.ctypes.data if want_sizes else None, C.byref(st), C.byref(ms))
+    else:
+        sizes = None
+        rc = lib().mpc_pattern_run_device(device, device_ptr, n_blocks, line_size, cache_blocks, None, C.byref(st), C.byref(ms))
+    if rc != 0:
+        raise MpcError(f"PATTERN failed ({rc}): {lib().mpc_pattern_error().decode()}")
+    return sizes, st, ms.value
 
 
 def unpack(packed):

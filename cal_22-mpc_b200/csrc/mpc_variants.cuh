@@ -70,7 +70,7 @@ MPC_HD uint64_t bdi_value(const uint32_t (&x)[32], int i) {  // little-endian ch
 // BDI::checkBDI, BDI.cpp:108-201: immediates (values that fit D bytes on their own), the first other value is the
 // base, every later one must be within a D-byte delta of it.
 template <int B, int D>
-MPC_HD uint32_t bdi_check(const uint32_t (&x)[32]) {
+MPC_HD uint32_t bdi_check(const uint32_t (&x)[32], uint32_t* imm_out = nullptr) {
   constexpr int n = 128 / B;
   uint32_t imm = 0;
   bool not_all = false;
@@ -108,6 +108,7 @@ MPC_HD uint32_t bdi_check(const uint32_t (&x)[32]) {
       not_all |= v > limit && !bdi_delta_fits32<D>(base, v);
     }
   }
+  if (imm_out) *imm_out = imm;
   if (not_all) return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)n - imm) * (uint32_t)B);
   return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)B + ((uint32_t)n - imm - 1u) * (uint32_t)D));  // wraps when imm == n
 }
@@ -136,6 +137,41 @@ MPC_HD uint32_t bdi_block(const uint32_t (&x)[32], int* state) {
   }
   *state = sel;
   return best + 4u;
+}
+
+// ---- PATTERN (analysis tool) --------------------------------------------------------------------------------------
+// Pattern::CompressLine, Pattern.cpp:6-75: the six base-delta checks in order (checkPattern, Pattern.cpp:109-199, is
+// checkBDI word for word), strict improvement wins, no zero / repeat shortcut.  *sel = PatternState 0..5, or 9
+// (NotDefined) when nothing beats the raw size; *imm = immediates of the selected check (countPattern,
+// Pattern.cpp:201-320: every immediate adds baseSize implicit bytes, every other value baseSize explicit bytes).
+// Returns bits incl. the 4 encoding bits.
+MPC_HD uint32_t pattern_block(const uint32_t (&x)[32], int* sel_out, uint32_t* imm_out) {
+  uint32_t best = 1024u, cur, im = 0, imm = 0;
+  int sel = 9;
+  // as in bdi_block: a check that fits has a constant size, so one that cannot beat the best so far is skipped
+  cur = bdi_check<8, 1>(x, &im); if (best > cur) { best = cur; sel = 0; imm = im; }
+  if (best > 320u) { cur = bdi_check<8, 2>(x, &im); if (best > cur) { best = cur; sel = 1; imm = im; } }
+  if (best > 560u) { cur = bdi_check<8, 4>(x, &im); if (best > cur) { best = cur; sel = 2; imm = im; } }
+  if (best > 312u) { cur = bdi_check<4, 1>(x, &im); if (best > cur) { best = cur; sel = 3; imm = im; } }
+  if (best > 560u) { cur = bdi_check<4, 2>(x, &im); if (best > cur) { best = cur; sel = 4; imm = im; } }
+  if (best > 584u) { cur = bdi_check<2, 1>(x, &im); if (best > cur) { best = cur; sel = 5; imm = im; } }
+  if (best == 1024u) sel = 9;
+  *sel_out = sel;
+  *imm_out = imm;
+  return best + 4u;
+}
+
+// 64-bit content hash of a block (temporal-locality pass: equal blocks are found by sorting the hashes, and every
+// match is confirmed on the 128 bytes themselves, so the hash only has to spread well)
+MPC_HD uint64_t block_hash64(const uint32_t (&x)[32]) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint64_t v = (uint64_t)x[2 * i] | ((uint64_t)x[2 * i + 1] << 32);
+    h = (h ^ v) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 29;
+  }
+  return mpcdev::splitmix64(h);
 }
 
 // ---- FPC ------------------------------------------------------------------------------------------------------

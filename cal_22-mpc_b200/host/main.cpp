@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "compressor/Pattern.h"
 #include "compressor/VPC.h"
 #include "compressor/Variants.h"
 #include "loader/LoaderGPGPU.h"
@@ -19,7 +20,7 @@
 
 static const char* kHelp =
     "\nUsage:\n  Compressor [OPTION...]\n\n"
-    "  -a, --algorithm arg  Compression algorithm [VPC/FPC/BDI/BPC/CPACK/SC2/VIEWER]. Default=VPC\n"
+    "  -a, --algorithm arg  Compression algorithm [VPC/FPC/BDI/BPC/CPACK/SC2/PATTERN/VIEWER]. Default=VPC\n"
     "  -i, --input arg      Input path. Supported extensions: .npy (memory dump), .log (GPGPU-Sim trace)\n"
     "  -c, --config arg     Config file path (.json).\n"
     "  -o, --output arg     Output directory path\n"
@@ -75,12 +76,13 @@ int main(int argc, char** argv) {
     compressor = new comp::VPC(configPath, gpus, kernel);  // main.cpp:88-91
   } else if (algorithm == "BDI" || algorithm == "FPC" || algorithm == "BPC" || algorithm == "CPACK" || algorithm == "SC2") {
     compressor = new comp::VariantCompressor(algorithm, lineSize, loader->GetNumLines());  // main.cpp:92-116
+  } else if (algorithm == "PATTERN") {
+    compressor = new comp::Pattern(lineSize);  // main.cpp:117-120
   } else if (algorithm == "VIEWER") {
     viewLines(loader);  // main.cpp:121-125: host only, no compressor
     return 0;
   } else {
-    // PATTERN (analysis tool, ratio always 0) is outside the compression path
-    printf("Invalid name of algorithm: \"%s\" (this build implements VPC, BDI, FPC, BPC, CPACK, SC2, VIEWER)\n", algorithm.c_str());
+    printf("Invalid name of algorithm: \"%s\" (this build implements VPC, BDI, FPC, BPC, CPACK, SC2, PATTERN, VIEWER)\n", algorithm.c_str());
     return 1;
   }
 

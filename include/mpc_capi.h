@@ -197,6 +197,29 @@ const char* mpc_sc2_error(void);
 int mpc_cpack_run_host(const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size, uint16_t* h_sizes,
                        mpc_variant_stats* out);
 
+/* PATTERN (analysis tool, Pattern.cpp:6-75, Pattern.h:34-231): bytes of all-zero lines, of lines repeating one 4-byte
+ * word, of lines seen before (temporal locality, LRU.h:17-56 with CACHESIZE = 2^24 - 1 lines), per base-delta layout
+ * (B8D1, B8D2, B8D4, B4D1, B4D2, B2D1) the implicit (immediate) and explicit bytes of the lines that chose it, bytes of
+ * lines no layout shrinks, and the byte histograms of all lines / of the lines that are neither all-zero nor
+ * word-repeating (Pattern.h:96-125; the report derives two entropies from them).  Replaces comp::Pattern::CompressLine
+ * + comp::PatternResult.  sizes (optional): the per-line return value (best layout + 4 bits).
+ * cache_blocks: capacity of the temporal-locality cache in lines, 0 = the reference's 2^24 - 1.
+ * temporal_path: 0 = device (hash sort; exact while the dump holds at most cache_blocks distinct lines), 1 = the cache
+ * was simulated in order on the host (more distinct lines than the cache holds: evictions make it sequential). */
+typedef struct {
+  uint64_t blocks, total_bytes;
+  uint64_t zeros_bytes, repeated_bytes, temporal_bytes, undefined_bytes;
+  uint64_t implicit_bytes[6], explicit_bytes[6];
+  uint64_t symbol_counts[256], symbol_counts_nontrivial[256];
+  uint64_t distinct_blocks;
+  int32_t temporal_path;
+} mpc_pattern_stats;
+int mpc_pattern_run_device(int device, const uint8_t* d_lines, uint64_t n_blocks, uint32_t line_size, uint64_t cache_blocks,
+                           uint16_t* d_sizes, mpc_pattern_stats* out, float* kernel_ms);
+int mpc_pattern_run_host(int device, const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size, uint64_t cache_blocks,
+                         uint16_t* h_sizes, mpc_pattern_stats* out, float* kernel_ms);
+const char* mpc_pattern_error(void);
+
 /* ---- library info ---------------------------------------------------------------------- */
 const char* mpc_version(void);
 

@@ -64,6 +64,21 @@ def oracle_sc2(lines, sampling, L=128):
     return sizes
 
 
+PATTERN_WORDS = 529  # layout: see orc_pattern_run in variants_oracle.c
+
+
+def oracle_pattern(lines, L=128, capacity=(1 << 24) - 1):
+    """CPU oracle of the PATTERN analysis: -> (sizes uint32 [n], stats uint64 [PATTERN_WORDS])"""
+    lines = np.ascontiguousarray(lines, dtype=np.uint8).reshape(-1, L)
+    sizes = np.zeros(lines.shape[0], dtype=np.uint32)
+    st = np.zeros(PATTERN_WORDS, dtype=np.uint64)
+    l = oracle_lib()
+    l.orc_pattern_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64, C.c_void_p, C.c_void_p]
+    l.orc_pattern_run.restype = None
+    l.orc_pattern_run(lines.ctypes.data, lines.shape[0], L, capacity, sizes.ctypes.data, st.ctypes.data)
+    return sizes, st
+
+
 VARIANT_ID = {"BDI": 1, "FPC": 2, "BPC": 3}
 
 
@@ -97,6 +112,10 @@ def ref_lib():
         l.ref_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         l.ref_vpc_print.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
         l.ref_vpc_print.restype = None
+        l.ref_pattern_stats.argtypes = [C.c_void_p, C.c_void_p]
+        l.ref_pattern_stats.restype = None
+        l.ref_pattern_print.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        l.ref_pattern_print.restype = None
         _ref = l
     return _ref
 
@@ -213,6 +232,14 @@ class RefCompressor:
         out = np.zeros(cap, dtype=np.uint64)
         n = ref_lib().ref_counts(self.h, out.ctypes.data, cap)
         return out[:n]
+
+    def pattern_stats(self):
+        out = np.zeros(PATTERN_WORDS, dtype=np.uint64)
+        ref_lib().ref_pattern_stats(self.h, out.ctypes.data)
+        return out
+
+    def pattern_print(self, workload, path):
+        ref_lib().ref_pattern_print(self.h, workload.encode(), os.fsencode(path))
 
     def vpc_print(self, workload, path, detail_path):
         ref_lib().ref_vpc_print(self.h, workload.encode(), os.fsencode(path), os.fsencode(detail_path))

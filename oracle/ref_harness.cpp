@@ -16,6 +16,7 @@
 #include "compressor/BPC.h"
 #include "compressor/CPACK.h"
 #include "compressor/SC2.h"
+#include "compressor/Pattern.h"
 
 namespace {
 struct Handle {
@@ -45,6 +46,7 @@ void* ref_create(const char* alg, const char* cfg, unsigned line_size, unsigned 
   else if (a == "BPC") h->c = new comp::BPC(line_size);
   else if (a == "CPACK") h->c = new comp::CPACK(line_size);
   else if (a == "SC2") h->c = new comp::SC2(line_size, sampling);
+  else if (a == "PATTERN") h->c = new comp::Pattern(line_size);
   else { delete h; return nullptr; }
   return h;
 }
@@ -123,6 +125,20 @@ int ref_counts(void* hv, uint64_t* out, int cap) {
     for (auto v : r->Counts) if (n < cap) out[n++] = v;
   }
   return n;
+}
+
+// PATTERN only: the counters of comp::PatternResult (Pattern.h:224-231) in the layout of orc_pattern_run
+// ([0] Z [1] R [2] T [3] U [4] Total [5..10] Implicit [11..16] Explicit [17..272] SymbolCounts [273..528] ...Except).
+void ref_pattern_stats(void* hv, uint64_t* out) {
+  auto* r = static_cast<comp::PatternResult*>(((Handle*)hv)->c->GetResult());
+  memset(out, 0, 529 * sizeof(uint64_t));
+  out[0] = r->Z; out[1] = r->R; out[2] = r->T; out[3] = r->U; out[4] = r->Total;
+  for (int i = 0; i < 6; i++) { out[5 + i] = r->ImplicitCounts[i]; out[11 + i] = r->ExplicitCounts[i]; }
+  for (auto& kv : r->SymbolCounts) out[17 + kv.first] = kv.second;
+  for (auto& kv : r->SymbolCountsExceptAllZerosAllWordSame) out[273 + kv.first] = kv.second;
+}
+void ref_pattern_print(void* hv, const char* workload, const char* path) {
+  static_cast<comp::PatternResult*>(((Handle*)hv)->c->GetResult())->Print(workload, path);
 }
 
 // Run Print/PrintDetail exactly as main.cpp:160-165 does for VPC.

@@ -309,3 +309,95 @@ void orc_sc2_run(const uint8_t* lines, uint64_t n, unsigned L, uint64_t sampling
     sizes[i] = s;
   }
 }
+
+/* ---- PATTERN (analysis tool): Pattern.cpp:6-75 (per line), 109-199 (checkPattern == checkBDI), 201-320 (countPattern),
+ * Pattern.h:62-125 (counters, byte histograms), LRU.h:17-56 (temporal locality).  isExistedBefore (Pattern.cpp:101-107)
+ * never promotes a hit (exist() does not touch the list) and inserts only on a miss, so the cache is a FIFO set of the
+ * last `capacity` distinct lines that missed (reference: CACHESIZE = 2^24 - 1, LRU.h:6).
+ * stats layout (uint64): [0] Z  [1] R  [2] T  [3] U  [4] Total  [5..10] Implicit  [11..16] Explicit
+ *                        [17..272] SymbolCounts  [273..528] SymbolCountsExceptAllZerosAllWordSame ------------------- */
+#include <stdlib.h>
+#define ORC_PATTERN_WORDS 529
+
+static uint64_t pat_hash(const uint8_t* line, unsigned L) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned i = 0; i < L; i++) { h ^= line[i]; h *= 1099511628211ull; }
+  return h ^ (h >> 29);
+}
+
+void orc_pattern_run(const uint8_t* lines, uint64_t n, unsigned L, uint64_t capacity, uint32_t* sizes, uint64_t* st) {
+  static const unsigned B[6] = {8, 8, 8, 4, 4, 2}, D[6] = {1, 2, 4, 1, 2, 1};
+  memset(st, 0, ORC_PATTERN_WORDS * sizeof(uint64_t));
+  /* FIFO set: open-addressing table of line indices (+1), tombstones on eviction, and the insertion order */
+  uint64_t slots = 16;
+  while (slots < 4 * (n < capacity ? n : capacity) + 16) slots <<= 1;
+  uint64_t* table = (uint64_t*)calloc(slots, sizeof(uint64_t)); /* 0 empty, ~0 tombstone, else index + 1 */
+  uint64_t* fifo = (uint64_t*)malloc((n ? n : 1) * sizeof(uint64_t));
+  uint64_t head = 0, tail = 0, live = 0, used = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    const uint8_t* line = lines + i * L;
+    int zero = 1, rep = 1;
+    for (unsigned k = 0; k < L; k++) if (line[k]) { zero = 0; break; }
+    for (unsigned k = 4; k < L; k++) if (line[k] != line[k % 4]) { rep = 0; break; } /* isRepeated(.., 4) */
+    if (zero) st[0] += L;
+    if (rep) st[1] += L;
+    { /* isExistedBefore */
+      uint64_t h = pat_hash(line, L), pos = h & (slots - 1), first_tomb = ~0ull;
+      int hit = 0;
+      while (table[pos] != 0) {
+        if (table[pos] == ~0ull) { if (first_tomb == ~0ull) first_tomb = pos; }
+        else if (memcmp(lines + (table[pos] - 1) * L, line, L) == 0) { hit = 1; break; }
+        pos = (pos + 1) & (slots - 1);
+      }
+      if (hit) {
+        st[2] += L;
+      } else {
+        if (first_tomb != ~0ull) pos = first_tomb; else used++;
+        table[pos] = i + 1;
+        fifo[tail++] = i;
+        live++;
+        while (live > capacity) { /* LRUCache::clean: drop the oldest inserted line */
+          const uint64_t victim = fifo[head++];
+          uint64_t p = pat_hash(lines + victim * L, L) & (slots - 1);
+          while (table[p] != victim + 1) p = (p + 1) & (slots - 1);
+          table[p] = ~0ull;
+          live--;
+        }
+        if (used * 2 > slots) { /* rebuild without tombstones */
+          memset(table, 0, slots * sizeof(uint64_t));
+          used = 0;
+          for (uint64_t q = head; q < tail; q++) {
+            uint64_t p = pat_hash(lines + fifo[q] * L, L) & (slots - 1);
+            while (table[p] != 0) p = (p + 1) & (slots - 1);
+            table[p] = fifo[q] + 1;
+            used++;
+          }
+        }
+      }
+    }
+    unsigned best = 8u * L, cur;
+    int sel = 9;
+    for (int k = 0; k < 6; k++) {
+      cur = bdi_check(line, L, B[k], D[k]);
+      if (best > cur) { sel = k; best = cur; }
+    }
+    if (best == 8u * L) sel = 9;
+    if (sel == 9) {
+      st[3] += L;
+    } else { /* countPattern: immediates are implicit bytes, everything else explicit */
+      const unsigned bs = B[sel], ds = D[sel], m = L / bs;
+      const uint64_t limit = ds == 1 ? 0xffull : ds == 2 ? 0xffffull : 0xffffffffull;
+      for (unsigned q = 0; q < m; q++) {
+        uint64_t t = 0;
+        for (int j = (int)bs - 1; j >= 0; j--) t = (t << 8) | line[q * bs + (unsigned)j];
+        if (bdi_reduce_sign(t) <= limit) st[5 + sel] += bs; else st[11 + sel] += bs;
+      }
+    }
+    for (unsigned k = 0; k < L; k++) st[17 + line[k]]++;
+    if (!(zero || rep)) for (unsigned k = 0; k < L; k++) st[273 + line[k]]++;
+    st[4] += L;
+    if (sizes) sizes[i] = best + 4u;
+  }
+  free(table);
+  free(fifo);
+}

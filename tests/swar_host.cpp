@@ -1,4 +1,5 @@
 // Host build of the SWAR primitives in csrc/mpc_device.cuh for exhaustive CPU checks (tests/test_swar_host.py).
+#include <string.h>
 #include "mpc_device.cuh"
 extern "C" {
 unsigned t_row2_cost(unsigned w, unsigned* nz) { return mpcdev::row2_cost(w, nz); }
@@ -54,4 +55,15 @@ extern "C" int t_bdi_fits_rule(unsigned long long x, int D) {
 }
 extern "C" int t_bdi_delta32(unsigned base, unsigned v, int D) {
   return D == 1 ? mpcvar::bdi_delta_fits32<1>(base, v) : mpcvar::bdi_delta_fits32<2>(base, v);
+}
+
+// PATTERN: per-block selection + immediates of the selected layout (mpcvar::pattern_block) and the content hash
+extern "C" void t_pattern_run(const unsigned char* lines, unsigned long long n, unsigned* sizes, int* sels, unsigned* imms,
+                              unsigned long long* hashes) {
+  for (unsigned long long i = 0; i < n; i++) {
+    uint32_t x[32];
+    memcpy(x, lines + i * 128, 128);
+    sizes[i] = mpcvar::pattern_block(x, &sels[i], &imms[i]);
+    hashes[i] = mpcvar::block_hash64(x);
+  }
 }
