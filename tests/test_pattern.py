@@ -131,7 +131,7 @@ def test_gpu_device_pointer_at_scale(mpcb):
     n = (256 << 20) // 128
     m = mpcb.Mpc(__import__("helpers").cfg_path("P6"))
     d = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
-    m.synth(d.data_ptr(), 0, n, n, "mixed_hashed", 77)
+    m.synth_device(d.data_ptr(), 0, n, n, "mixed_hashed", 77)
     _, whole, ms = mpcb.pattern_run(device_ptr=d.data_ptr(), n_blocks=n)
     _, a, _ = mpcb.pattern_run(device_ptr=d.data_ptr(), n_blocks=n // 2)
     _, b, _ = mpcb.pattern_run(device_ptr=d.data_ptr() + (n // 2) * 128, n_blocks=n - n // 2)
