@@ -47,6 +47,10 @@ def main():
         rc = mpcb.lib().mpc_sc2_run_device(0, d.data_ptr(), n, 128, S, None, C.byref(vs), C.byref(msf))
         assert rc == 0, mpcb.lib().mpc_sc2_error()
     rows.append({"alg": f"SC2 (S={S}, incl. sort + host tree)", "gbs": n * 128 / msf.value / 1e6, "ratio": vs.original_bits / vs.compressed_bits, "where": "GPU+host tree"})
+    for rep in range(2):
+        _, ps, ms = mpcb.pattern_run(device_ptr=d.data_ptr(), n_blocks=n)
+    rows.append({"alg": f"PATTERN (analysis; {ps.distinct_blocks} distinct lines, temporal path {ps.temporal_path})", "gbs": n * 128 / ms / 1e6,
+                 "ratio": 0.0, "where": "GPU (kernel + hash sort)"})
     nc = min(n, (a.cpack_mib << 20) // 128)
     host = d[: nc * 128].cpu().numpy()
     t0 = time.perf_counter()
