@@ -34,6 +34,9 @@ struct Driver {
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;  // optional: programmatic dependent launch
+  CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
   bool ok = false;
 };
 
@@ -55,6 +58,7 @@ Driver& driver() {
            entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", &d.OccupancyMaxActiveBlocksPerMultiprocessor) &&
            entry("cuLaunchKernel", &d.LaunchKernel);
     entry("cuLaunchKernelEx", &d.LaunchKernelEx);
+    entry("cuTensorMapEncodeTiled", &d.TensorMapEncodeTiled);
   });
   return d;
 }
@@ -149,6 +153,20 @@ void jit_destroy(JitKernel* k) {
   delete k;
 }
 
+cudaError_t make_tile_tmap(TileTmap* out, const uint8_t* d_lines, uint64_t n_blocks) {
+  static_assert(sizeof(TileTmap) == sizeof(CUtensorMap), "TileTmap must be a CUtensorMap");
+  if (!driver().TensorMapEncodeTiled) return cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {128, n_blocks};          // innermost first: 128 bytes per block, n_blocks rows
+  const cuuint64_t strides[1] = {128};                 // bytes between rows
+  const cuuint32_t box[2] = {128, 32};                 // one tile: 32 blocks
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = driver().TensorMapEncodeTiled(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                                                   const_cast<uint8_t*>(d_lines), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 int jit_lut_xor(const JitKernel* k) { return k->traits.use_lut ? k->traits.lut_xor : 0; }
 
 cudaError_t jit_launch(JitKernel* k, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed, uint64_t* d_stats,
@@ -165,7 +183,15 @@ cudaError_t jit_launch(JitKernel* k, const uint8_t* d_lines, uint64_t n_blocks, 
   const uint64_t total_warps = grid * (uint64_t)k->traits.warps;
   unsigned int static_rounds = eighths == 8 ? (unsigned int)((n_tiles + total_warps - 1) / total_warps)
                                             : (unsigned int)((n_tiles / total_warps) * (uint64_t)eighths / 8);
-  void* args[] = {(void*)&d_lines, (void*)&n, (void*)&d_packed, (void*)&d_stats, (void*)&d_row_lut, (void*)&d_sched, (void*)&static_rounds};
+  TileTmap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (k->traits.tma) {
+    if (n_blocks >= (1ull << 31)) return cudaErrorInvalidValue;  // tensor coordinates are signed 32-bit
+    const cudaError_t te = make_tile_tmap(&tmap, d_lines, n_blocks);
+    if (te != cudaSuccess) return te;
+  }
+  void* args[] = {(void*)&d_lines, (void*)&n, (void*)&d_packed, (void*)&d_stats, (void*)&d_row_lut, (void*)&d_sched, (void*)&static_rounds,
+                  (void*)&tmap};
   CUresult r;
   const char* pdl = getenv("MPC_PDL");
   if (driver().LaunchKernelEx && !(pdl && pdl[0] == '0')) {

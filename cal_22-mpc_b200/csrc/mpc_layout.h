@@ -11,4 +11,8 @@ constexpr unsigned long long kStatsWords = 2ull * kK + (unsigned long long)kK * 
 constexpr unsigned long long kResAbsOff = 0;
 constexpr unsigned long long kResSqOff = kK;
 constexpr unsigned long long kHistOff = 2 * kK;
+// A CUtensorMap (128 bytes, 64-byte aligned) as the kernels see it: opaque, so that the NVRTC build needs no cuda.h.
+// Describes the dump as a [n_blocks][128 B] uint8 tensor with a 32 x 128 B box and the 128-byte swizzle
+// (make_tile_tmap, mpc_jit.cpp).
+struct alignas(64) TileTmap { unsigned long long opaque[16]; };
 }  // namespace mpc

@@ -617,7 +617,9 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   e = getenv("MPC_SPEC_SKIP");
   t.skip_zero_groups = e ? (e[0] != '0') : !t.use_lut;
   if ((e = getenv("MPC_SPEC_STAGES")) && (atoi(e) == 1 || atoi(e) == 2)) t.stages = atoi(e);
-  t.smem_bytes = (size_t)t.warps * t.stages * 4096 + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
+  // tile loader: one TMA tensor copy per warp and tile (SWIZZLE_128B = the layout the per-thread reads want) when the warp has one stage
+  t.tma = t.stages == 1 && !((e = getenv("MPC_SPEC_TMA")) && e[0] == '0');
+  t.smem_bytes = (size_t)t.warps * t.stages * 4096 + (t.tma ? (size_t)((t.warps * 8 + 15) / 16) * 16 : 0) + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
                  (t.use_lut ? 65536 : 0);
   return t;
 }
@@ -671,6 +673,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   // tile stages and the histogram fit the 227 KiB of shared memory
   out.push_back(fmt("  static constexpr int kWarps = %d;", t.warps));
   out.push_back(fmt("  static constexpr int kStages = %d;  // shared-memory tile stages per warp", t.stages));
+  out.push_back(fmt("  static constexpr bool kTma = %s;  // tiles arrive by TMA (cp.async.bulk.tensor, one per warp and tile) instead of cp.async", t.tma ? "true" : "false"));
   out.push_back(fmt("  static constexpr bool kUseLut = %s;  // shared-memory row-cost table (column-major modules)", t.use_lut ? "true" : "false"));
   out.push_back(fmt("  static constexpr bool kSkipZeroGroups = %s;  // branch around groups of eight zero rows in the encoder", t.skip_zero_groups ? "true" : "false"));
   out.push_back(fmt("  static constexpr int kLutXor = %d;  // 0: table indexed by scan rows; 1 / 2: XOR stage (consecutive / first-plane) folded into the table",
@@ -737,8 +740,8 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     out.push_back(fmt("extern \"C\" __global__ void __launch_bounds__(mpc::spec_%s::Cfg::kWarps * 32, mpc::spec_%s::Cfg::kMinCtasPerSm)", name.c_str(), name.c_str()));
     out.push_back("mpc_jit_kernel(const uint4* __restrict__ lines, unsigned long long n_blocks, unsigned short* __restrict__ packed,");
     out.push_back("               unsigned long long* __restrict__ stats, const uint4* __restrict__ row_lut, unsigned int* __restrict__ sched,");
-    out.push_back("               unsigned int static_rounds) {");
-    out.push_back(fmt("  mpc::spec::spec_kernel_body<mpc::spec_%s::Cfg>(lines, n_blocks, packed, stats, row_lut, sched, static_rounds);", name.c_str()));
+    out.push_back("               unsigned int static_rounds, const __grid_constant__ mpc::TileTmap tmap) {");
+    out.push_back(fmt("  mpc::spec::spec_kernel_body<mpc::spec_%s::Cfg>(lines, n_blocks, packed, stats, row_lut, sched, static_rounds, &tmap);", name.c_str()));
     out.push_back("}");
   } else {
     out.push_back("static const mpc_config_pod kPod =");

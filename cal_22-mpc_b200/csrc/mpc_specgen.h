@@ -15,6 +15,7 @@ struct SpecTraits {
   int stages = 2;                // shared-memory tile stages per warp (1: the registers are the second buffer)
   int min_ctas = 2;              // __launch_bounds__ second argument
   bool skip_zero_groups = true;  // encoder branches around groups of eight zero rows
+  bool tma = false;              // tiles arrive by one TMA tensor copy per warp (cp.async.bulk.tensor + mbarrier) instead of 8 cp.async per lane
   size_t smem_bytes = 0;         // dynamic shared memory of one CTA
 };
 
