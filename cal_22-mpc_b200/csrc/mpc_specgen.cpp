@@ -617,8 +617,11 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   e = getenv("MPC_SPEC_SKIP");
   t.skip_zero_groups = e ? (e[0] != '0') : !t.use_lut;
   if ((e = getenv("MPC_SPEC_STAGES")) && (atoi(e) == 1 || atoi(e) == 2)) t.stages = atoi(e);
-  // tile loader: one TMA tensor copy per warp and tile (SWIZZLE_128B = the layout the per-thread reads want) when the warp has one stage
-  t.tma = t.stages == 1 && !((e = getenv("MPC_SPEC_TMA")) && e[0] == '0');
+  // tile loader: MPC_SPEC_TMA=1 selects one TMA tensor copy per warp and tile (cp.async.bulk.tensor 2D, SWIZZLE_128B = the layout the
+  // per-thread reads want, completion on a per-warp mbarrier) instead of 8 cp.async per lane.  Bit-exact, but measured slower on B200
+  // (F4 smooth 4 300 -> 4 020 GB/s, random 4 035 -> 3 785; 2.5 points of it are the fence.proxy.async that must order the warp's reads
+  // of the stage before the next copy), so cp.async stays the default.
+  t.tma = t.stages == 1 && (e = getenv("MPC_SPEC_TMA")) && e[0] == '1';
   t.smem_bytes = (size_t)t.warps * t.stages * 4096 + (t.tma ? (size_t)((t.warps * 8 + 15) / 16) * 16 : 0) + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
                  (t.use_lut ? 65536 : 0);
   return t;

@@ -75,3 +75,28 @@ def test_jit_can_be_disabled(mpcb, monkeypatch):
     with pytest.raises(mpcb.MpcError) as e:
         m.set_kernel(2)
     assert "MPC_JIT=0" in str(e.value)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1, 4])
+def test_jit_kernels_with_the_tma_tile_loader_match_oracle(mpcb, monkeypatch, seed):
+    """MPC_SPEC_TMA=1: tiles arrive by cp.async.bulk.tensor (2D tensor map, 128-byte swizzle, per-warp mbarrier) instead
+    of cp.async; ragged block counts exercise the zero-filled rows past the end of the dump."""
+    monkeypatch.setenv("MPC_SPEC_TMA", "1")
+    monkeypatch.setenv("MPC_JIT_CACHE_DIR", "")
+    cfg = eligible_config(200 + seed)
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(cfg)))
+    assert m.kernel_name() == "spec_thread:jit"
+    rng = np.random.default_rng(seed)
+    for n in (1, 31, 33, 2999):
+        blocks = random_blocks(rng, n)
+        sizes, sels, st = m.compress(blocks)
+        r = OracleMPC(cfg).run(blocks)
+        assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels), n
+        assert st.CompressedSize == r.CompressedSize and np.array_equal(st.res_abs, r.res_abs)
+
+
+def test_tma_variant_compiles_with_nvrtc(mpcb, monkeypatch):
+    monkeypatch.setenv("MPC_SPEC_TMA", "1")
+    rc, nbytes, log = mpcb.jit_compile_check(cfg_path("F4"))
+    assert rc == 0 and nbytes > 10000, log
