@@ -25,7 +25,8 @@ $(CSRC)/spec/.stamp: tools/specgen $(foreach c,$(SPEC_CFGS),configs/$(c).json)
 	@mkdir -p $(CSRC)/spec
 	tools/specgen $(CSRC)/spec $(foreach c,$(SPEC_CFGS),configs/$(c).json)
 	@touch $@
-$(SPEC_SRCS) $(CSRC)/spec/spec_list.inc: $(CSRC)/spec/.stamp
+# the empty recipe (";") makes make re-read the time stamps of the generated sources after the generator ran
+$(SPEC_SRCS) $(CSRC)/spec/spec_list.inc: $(CSRC)/spec/.stamp ;
 
 $(CSRC)/mpc_spec_list.o: $(CSRC)/spec/spec_list.inc
 
