@@ -190,6 +190,11 @@ struct DevBuf {
   void* p = nullptr;
   ~DevBuf() { if (p) cudaFree(p); }
 };
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
 
 }  // namespace
 }  // namespace mpc
@@ -203,7 +208,7 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
   if (!out || (n_blocks && !d_lines)) return pfail(MPC_E_ARG, "null argument");
   if (line_size != 128) return pfail(MPC_E_ARG, "the GPU pattern analysis is built for 128-byte blocks");
   if ((uintptr_t)d_lines & 15) return pfail(MPC_E_ARG, "lines must be 16-byte aligned");
-  if (n_blocks >= 0xffffffffull) return pfail(MPC_E_ARG, "too many blocks for 32-bit line indices");
+  if (n_blocks >= (1ull << 31)) return pfail(MPC_E_ARG, "too many blocks for 32-bit line indices");
   if (cache_blocks == 0) cache_blocks = (1ull << 24) - 1;  // CACHESIZE, LRU.h:6
   PAT_CUDA(cudaSetDevice(device));
   int sms = 148;
@@ -213,10 +218,8 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
   PAT_CUDA(cudaMalloc(&stats.p, kWords * sizeof(unsigned long long)));
   PAT_CUDA(cudaMemset(stats.p, 0, kWords * sizeof(unsigned long long)));
   PAT_CUDA(cudaMalloc(&keys.p, (size_t)(n ? n : 1) * 8));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventRecord(e0, 0);
+  EventPair ev;
+  cudaEventRecord(ev.a, 0);
   if (n) {
     const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
     PAT_CUDA(cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -245,13 +248,11 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
                                          (unsigned long long*)stats.p);
     PAT_CUDA(cudaGetLastError());
   }
-  cudaEventRecord(e1, 0);
+  cudaEventRecord(ev.b, 0);
   std::vector<unsigned long long> h(kWords);
   PAT_CUDA(cudaMemcpy(h.data(), stats.p, kWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  cudaEventElapsedTime(&ms, ev.a, ev.b);
 
   memset(out, 0, sizeof(*out));
   static const uint32_t kBase[6] = {8, 8, 8, 4, 4, 2};
