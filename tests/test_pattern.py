@@ -24,6 +24,28 @@ def dump_with_repeats(seed=5, n=6000):
     return np.concatenate([d, d[idx], random_blocks(rng, 500), d[idx[::-1]]])
 
 
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_case():
+    """the dump of tests/golden/make_golden_pattern.py and what the unmodified reference produced for it"""
+    sys_path_golden = os.path.join(ROOT, "tests", "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_pattern", os.path.join(sys_path_golden, "make_golden_pattern.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(GOLD, "pattern.npz"))
+    d = mod.pattern_dump()
+    assert d.shape[0] == int(g["n"][0])
+    return d, g["sizes"].astype(np.uint32), g["stats"]
+
+
+def test_oracle_matches_committed_reference_fixture():
+    d, sizes, stats = golden_case()
+    got_sizes, got_stats = oracle_pattern(d)
+    assert np.array_equal(got_sizes, sizes) and np.array_equal(got_stats, stats)
+
+
 def test_oracle_known_answers():
     sizes, st = oracle_pattern(kat_blocks())
     assert sizes.tolist() == KAT
@@ -104,6 +126,25 @@ def test_gpu_known_answers_and_classes(mpcb):
     st = check_against_oracle(mpcb, dump_with_repeats())
     assert st.temporal_path == 0 and st.temporal_bytes > 0
     assert st.distinct_blocks == len(np.unique(dump_with_repeats(), axis=0))
+
+
+@pytest.mark.gpu
+def test_gpu_matches_committed_reference_fixture(mpcb, tmp_path):
+    """library and CLI against tests/golden (generated from the unmodified reference): per-line values, counters, CSV bytes"""
+    d, sizes, stats = golden_case()
+    got, st, _ = mpcb.pattern_run(d)
+    assert np.array_equal(got.astype(np.uint32), sizes) and np.array_equal(st.words(), stats)
+    ds = tmp_path / "ds"
+    out = tmp_path / "out"
+    ds.mkdir()
+    out.mkdir()
+    np.save(ds / "pattern_set.npy", np.concatenate([d, np.zeros((1, 128), np.uint8)]))
+    for _ in range(2):  # appended twice, like the fixture: header + 2 rows
+        r = subprocess.run([os.path.join(ROOT, "bin", "compressor"), "-a", "PATTERN", "-i", str(ds / "pattern_set.npy"), "-o", str(out)],
+                           capture_output=True, text=True, check=True)
+    assert r.stdout == open(os.path.join(GOLD, "cli_PATTERN_stdout.txt")).read()
+    assert (out / "PATTERN_results.csv").read_bytes() == open(os.path.join(GOLD, "cli_PATTERN_results.csv"), "rb").read()
+    assert not (out / "PATTERN_results_detail.csv").exists()
 
 
 @pytest.mark.gpu
