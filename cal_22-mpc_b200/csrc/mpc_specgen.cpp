@@ -233,7 +233,7 @@ struct Module {
     std::string e;
     int a = 0, b = 0;
     if (shared_low && plain_word(xe, &a) && plain_word(pe, &b))
-      e = fmt("sub_u8x4_shared(x[%d], x[%d], al[%d], al[%d])", a, b, a, b);
+      e = fmt("sub_u8x4_shared(x[%d], x[%d], ah[%d], ah[%d])", a, b, a, b);
     else
       e = fmt("sub_u8x4(%s, %s)", xe.c_str(), pe.c_str());
     if (w == 0) e = fmt("((%s & 0xffffff00u) | %s)", e.c_str(), root_byte().c_str());
@@ -361,9 +361,9 @@ void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay) {
   out.push_back(fmt("__device__ __forceinline__ void full_%d(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq) {", m.idx));
   out.push_back("  uint32_t g[32];");
   out.push_back("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one");
-  out.push_back("  uint32_t al[32];");
+  out.push_back("  uint32_t ah[32];");
   out.push_back("#pragma unroll");
-  out.push_back("  for (int i = 0; i < 32; i++) al[i] = x[i] & 0x7f7f7f7fu;  // only the words a plain-copy predictor uses survive");
+  out.push_back("  for (int i = 0; i < 32; i++) ah[i] = x[i] | 0x80808080u;  // only the words a plain-copy predictor uses survive");
   for (int w = 0; w < W; w++) {
     out.push_back("  { " + m.residue_stmts(w, "r", true));
     if (w == 0) {
