@@ -16,7 +16,11 @@ CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CS
 CU_OBJS  := $(CU_SRCS:.cu=.o)
 CC_OBJS  := $(CSRC)/mpc_config.o $(CSRC)/mpc_specgen.o $(CSRC)/mpc_jit.o
 
-all: $(LIB) compressor oracle
+all: $(LIB) compressor oracle tools/int_peak
+
+# integer-pipe issue-rate micro-benchmark (roofline B); bench.py runs it on the GPU box
+tools/int_peak: tools/int_peak.cu
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 
 # config compiler (csrc/mpc_specgen.cpp): one specialised schedule per shipped config; generated sources are committed
 tools/specgen: tools/specgen_main.cpp $(CSRC)/mpc_specgen.cpp $(CSRC)/mpc_specgen.h $(CSRC)/mpc_config.cpp include/mpc_capi.h
@@ -47,21 +51,22 @@ $(CSRC)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h include/*.h)
 	$(CXX) $(CXXFLAGS) -I/usr/local/cuda/include -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(CC_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -lnvrtc -Xlinker --no-undefined -Xlinker -rpath=/usr/local/cuda/lib64
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -lnvrtc -ldl -Xlinker --no-undefined -Xlinker -rpath=/usr/local/cuda/lib64
 
 HOST_SRCS := $(wildcard $(HOST)/*.cpp $(HOST)/compressor/*.cpp $(HOST)/loader/*.cpp)
 compressor: bin/compressor
 bin/compressor: $(HOST_SRCS) $(wildcard $(HOST)/*.h $(HOST)/compressor/*.h $(HOST)/loader/*.h) $(LIB)
 	@mkdir -p bin; if [ -n "$(HOST_SRCS)" ]; then \
 	  $(CXX) $(CXXFLAGS) -I$(HOST) -I/usr/local/cuda/include $(HOST_SRCS) -o bin/compressor -L$(PKG) -lmpc_b200 \
-	    -L/usr/local/cuda/lib64 -lcudart -lnccl -Wl,-rpath,'$$ORIGIN/../$(PKG)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread; \
+	    -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(PKG)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread; \
 	fi
 
 oracle:
 	$(MAKE) -C oracle
 
+# SASS of the specialised kernels' hot loops for profiles/ (one listing per shipped config)
 sass: $(LIB)
-	cuobjdump -sass $(LIB) > profiles/libmpc_b200.sass
+	python3 tools/sass_listing.py
 
 clean:
 	rm -f $(CSRC)/*.o $(CSRC)/spec/*.o $(LIB) bin/compressor tools/specgen

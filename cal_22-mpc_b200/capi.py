@@ -13,6 +13,7 @@ MAX_LINE = 128
 MAX_MODULES = 16
 HIST_BINS = 8 * MAX_LINE + 32
 STATS_WORDS = 2 * (MAX_MODULES + 1) + (MAX_MODULES + 1) * HIST_BINS
+COMM_UID_BYTES = 128
 
 SYN = {"zero": 0, "wordsame": 1, "smooth_f32": 2, "ramp_i32": 3, "pointer": 4, "random": 5,
        "sparse_i32": 6, "noisy_f32": 7, "mixed_hashed": 8, "mixed_regions": 9}
@@ -77,7 +78,9 @@ SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config
            "mpc_stats_expand", "mpc_reset", "mpc_last_timing", "mpc_synth_device", "mpc_version",
            "mpc_variant_run_device", "mpc_variant_run_host", "mpc_variant_error", "mpc_sc2_run_device", "mpc_sc2_run_host",
            "mpc_sc2_error", "mpc_cpack_run_host", "mpc_jit_compile_check", "mpc_enable_timing",
-           "mpc_pattern_run_device", "mpc_pattern_run_host", "mpc_pattern_error"]
+           "mpc_pattern_run_device", "mpc_pattern_run_host", "mpc_pattern_error",
+           "mpc_comm_unique_id", "mpc_comm_init_rank", "mpc_comm_init_all", "mpc_attach_comm", "mpc_allreduce_stats",
+           "mpc_reduced_stats", "mpc_reduced_device_ptr", "mpc_finish_allreduce"]
 
 
 def lib():
@@ -123,6 +126,14 @@ def lib():
     l.mpc_pattern_run_device.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(PatternStats), C.POINTER(C.c_float)]
     l.mpc_pattern_run_host.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(PatternStats), C.POINTER(C.c_float)]
     l.mpc_pattern_error.restype = C.c_char_p
+    l.mpc_comm_unique_id.argtypes = [vp, sz]
+    l.mpc_comm_init_rank.argtypes = [vp, vp, sz, C.c_int, C.c_int]
+    l.mpc_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
+    l.mpc_attach_comm.argtypes = [vp, vp]
+    l.mpc_allreduce_stats.argtypes = [C.POINTER(vp), C.c_int]
+    l.mpc_reduced_stats.argtypes = [vp, C.POINTER(StatsPod)]
+    l.mpc_reduced_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    l.mpc_finish_allreduce.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(StatsPod)]
     _LIB = l
     return l
 
@@ -246,6 +257,34 @@ class Mpc:
         words = np.ascontiguousarray(words, dtype=np.uint64)
         pod = StatsPod()
         self._check(lib().mpc_stats_expand(C.byref(self.cfg), words.ctypes.data, words.size, C.byref(pod)))
+        return Stats(pod, self.cfg.num_modules, self.line_size)
+
+    # ---- multi-GPU: the statistics all-reduce behind the ABI (one context per rank) ----
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(COMM_UID_BYTES)
+        rc = lib().mpc_comm_unique_id(buf, COMM_UID_BYTES)
+        if rc != 0:
+            raise MpcError(f"mpc_comm_unique_id failed ({rc}): {lib().mpc_global_error().decode()}")
+        return buf.raw
+
+    def comm_init_rank(self, uid, nranks, rank):
+        self._check(lib().mpc_comm_init_rank(self.h, uid, len(uid), nranks, rank))
+
+    def allreduce_stats(self):
+        """asynchronous on the context's stream: all-reduce a copy of the statistics vector"""
+        arr = (C.c_void_p * 1)(self.h)
+        self._check(lib().mpc_allreduce_stats(arr, 1))
+
+    def reduced_stats(self):
+        pod = StatsPod()
+        self._check(lib().mpc_reduced_stats(self.h, C.byref(pod)))
+        return Stats(pod, self.cfg.num_modules, self.line_size)
+
+    def finish_allreduce(self):
+        pod = StatsPod()
+        arr = (C.c_void_p * 1)(self.h)
+        self._check(lib().mpc_finish_allreduce(arr, 1, C.byref(pod)))
         return Stats(pod, self.cfg.num_modules, self.line_size)
 
     def last_timing(self):

@@ -2,10 +2,14 @@
 // the statistics vector.  Replaces the per-line driver loop of the reference
 // (src/main.cpp:229-244: GetCacheline -> CompressLine -> VPCResult::Update) with batched launches.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library resolves the NCCL entry points with dlopen when a communicator is first used
+#include <unistd.h>
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -59,6 +63,11 @@ struct mpc_ctx {
   std::string error;
   std::string kernel_name;
   std::string jit_note;  // why no specialised kernel exists for this context, if that is the case
+  // multi-GPU: the job's one collective is an all-reduce of the statistics vector
+  ncclComm_t comm = nullptr;
+  bool comm_owned = false;                // created by mpc_comm_init_rank / mpc_comm_init_all: destroyed with the context
+  uint64_t* d_reduced = nullptr;          // all-reduced copy of d_stats (d_stats itself keeps accumulating locally)
+  bool stages_ready = false;              // every buffer of both mpc_submit_host stages exists
 };
 
 namespace {
@@ -133,20 +142,108 @@ void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t bytes) {
   for (auto& t : th) t.join();
 }
 
+void free_stages(mpc_ctx* ctx) {
+  for (Stage& st : ctx->stage) {
+    if (st.stream) cudaStreamDestroy(st.stream);
+    if (st.h_pinned) cudaFreeHost(st.h_pinned);
+    if (st.d_lines) cudaFree(st.d_lines);
+    if (st.d_packed) cudaFree(st.d_packed);
+    if (st.h_packed) cudaFreeHost(st.h_packed);
+    if (st.k_start) cudaEventDestroy(st.k_start);
+    if (st.k_stop) cudaEventDestroy(st.k_stop);
+    if (st.done) cudaEventDestroy(st.done);
+    st = Stage();
+  }
+  ctx->stages_ready = false;
+}
+
 int ensure_stages(mpc_ctx* ctx) {
-  if (ctx->stage[0].stream) return MPC_OK;
+  if (ctx->stages_ready) return MPC_OK;
+  free_stages(ctx);  // a previous attempt may have failed half way: start from nothing
   ctx->chunk_blocks = (64ull << 20) / (uint64_t)ctx->cfg.line_size;  // 64 MiB per chunk
   const size_t bytes = (size_t)ctx->chunk_blocks * ctx->cfg.line_size;
-  for (Stage& st : ctx->stage) {
-    MPC_CUDA(ctx, cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
-    MPC_CUDA(ctx, cudaMallocHost(&st.h_pinned, bytes));
-    MPC_CUDA(ctx, cudaMalloc(&st.d_lines, bytes));
-    MPC_CUDA(ctx, cudaMalloc(&st.d_packed, ctx->chunk_blocks * sizeof(uint16_t)));
-    MPC_CUDA(ctx, cudaMallocHost(&st.h_packed, ctx->chunk_blocks * sizeof(uint16_t)));
-    MPC_CUDA(ctx, cudaEventCreate(&st.k_start));
-    MPC_CUDA(ctx, cudaEventCreate(&st.k_stop));
-    MPC_CUDA(ctx, cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  auto alloc = [&]() -> cudaError_t {
+    cudaError_t e;
+    for (Stage& st : ctx->stage) {
+      if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+      if ((e = cudaMallocHost(&st.h_pinned, bytes)) != cudaSuccess) return e;
+      if ((e = cudaMalloc(&st.d_lines, bytes)) != cudaSuccess) return e;
+      if ((e = cudaMalloc(&st.d_packed, ctx->chunk_blocks * sizeof(uint16_t))) != cudaSuccess) return e;
+      if ((e = cudaMallocHost(&st.h_packed, ctx->chunk_blocks * sizeof(uint16_t))) != cudaSuccess) return e;
+      if ((e = cudaEventCreate(&st.k_start)) != cudaSuccess) return e;
+      if ((e = cudaEventCreate(&st.k_stop)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  const cudaError_t e = alloc();
+  if (e != cudaSuccess) {
+    free_stages(ctx);
+    return fail(ctx, MPC_E_CUDA, "allocating the host-submit stages failed: %s", cudaGetErrorString(e));
   }
+  ctx->stages_ready = true;
+  return MPC_OK;
+}
+
+// ---- NCCL, resolved at run time: a single-GPU user never loads it, and under torchrun the process-wide libnccl.so.2
+// (torch's) is the one that gets used --------------------------------------------------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names)
+      if ((api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!api.handle) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+#define MPC_NCCL_SYM(field, name)                                                   \
+  *(void**)(&api.field) = dlsym(api.handle, name);                                  \
+  if (!api.field) { api.error = std::string("libnccl lacks ") + name; return; }
+    MPC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    MPC_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    MPC_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+    MPC_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    MPC_NCCL_SYM(CommCount, "ncclCommCount")
+    MPC_NCCL_SYM(AllReduce, "ncclAllReduce")
+    MPC_NCCL_SYM(GroupStart, "ncclGroupStart")
+    MPC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    MPC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef MPC_NCCL_SYM
+  });
+  return &api;
+}
+
+#define MPC_NCCL(ctx, api, call)                                                                                 \
+  do {                                                                                                           \
+    ncclResult_t r__ = (call);                                                                                   \
+    if (r__ != ncclSuccess) return fail(ctx, MPC_E_CUDA, "%s failed: %s", #call, (api)->GetErrorString(r__));    \
+  } while (0)
+
+// NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO is set (this image sets it); the CLI's stdout
+// carries exactly what the reference prints, so the banner is sent to stderr while a communicator initialises.
+struct StdoutToStderr {
+  int saved = -1;
+  StdoutToStderr() { fflush(stdout); saved = dup(1); if (saved >= 0) dup2(2, 1); }
+  ~StdoutToStderr() { if (saved >= 0) { fflush(stdout); dup2(saved, 1); close(saved); } }
+};
+
+int ensure_reduced(mpc_ctx* ctx) {
+  if (ctx->d_reduced) return MPC_OK;
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPC_CUDA(ctx, cudaMalloc(&ctx->d_reduced, mpc::kStatsWords * sizeof(uint64_t)));
   return MPC_OK;
 }
 
@@ -228,16 +325,12 @@ void mpc_destroy(mpc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  for (Stage& st : ctx->stage) {
-    if (st.stream) cudaStreamDestroy(st.stream);
-    if (st.h_pinned) cudaFreeHost(st.h_pinned);
-    if (st.d_lines) cudaFree(st.d_lines);
-    if (st.d_packed) cudaFree(st.d_packed);
-    if (st.h_packed) cudaFreeHost(st.h_packed);
-    if (st.k_start) cudaEventDestroy(st.k_start);
-    if (st.k_stop) cudaEventDestroy(st.k_stop);
-    if (st.done) cudaEventDestroy(st.done);
+  if (ctx->comm && ctx->comm_owned) {
+    NcclApi* api = nccl_api();
+    if (api->CommDestroy) api->CommDestroy(ctx->comm);
   }
+  if (ctx->d_reduced) cudaFree(ctx->d_reduced);
+  free_stages(ctx);
   if (ctx->d_gmods) cudaFree(ctx->d_gmods);
   if (ctx->d_row_lut) cudaFree(ctx->d_row_lut);
   if (ctx->jit) mpc::jit_destroy(ctx->jit);
@@ -424,6 +517,133 @@ int mpc_last_timing(mpc_ctx* ctx, float* kernel_ms, int* launches) {
   if (kernel_ms) *kernel_ms = ctx->last_ms;
   if (launches) *launches = ctx->last_launches;
   return MPC_OK;
+}
+
+
+/* ---- multi-GPU: the statistics all-reduce behind the ABI ------------------------------------------------------- */
+
+int mpc_comm_unique_id(void* uid, size_t uid_len) {
+  if (!uid || uid_len < sizeof(ncclUniqueId)) return fail(nullptr, MPC_E_ARG, "mpc_comm_unique_id: need %zu bytes", sizeof(ncclUniqueId));
+  NcclApi* api = nccl_api();
+  if (!api->error.empty()) return fail(nullptr, MPC_E_STATE, "%s", api->error.c_str());
+  ncclUniqueId id;
+  MPC_NCCL(nullptr, api, api->GetUniqueId(&id));
+  memcpy(uid, &id, sizeof(id));
+  return MPC_OK;
+}
+
+int mpc_comm_init_rank(mpc_ctx* ctx, const void* uid, size_t uid_len, int nranks, int rank) {
+  if (!ctx || !uid || uid_len < sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks)
+    return fail(ctx, MPC_E_ARG, "mpc_comm_init_rank: bad argument");
+  if (ctx->comm) return fail(ctx, MPC_E_STATE, "mpc_comm_init_rank: the context already has a communicator");
+  NcclApi* api = nccl_api();
+  if (!api->error.empty()) return fail(ctx, MPC_E_STATE, "%s", api->error.c_str());
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, uid, sizeof(id));
+  {
+    StdoutToStderr quiet;
+    MPC_NCCL(ctx, api, api->CommInitRank(&ctx->comm, nranks, id, rank));
+  }
+  ctx->comm_owned = true;
+  return ensure_reduced(ctx);
+}
+
+int mpc_comm_init_all(mpc_ctx** ctxs, int n) {
+  if (!ctxs || n < 1) return fail(nullptr, MPC_E_ARG, "mpc_comm_init_all: bad argument");
+  for (int i = 0; i < n; i++)
+    if (!ctxs[i] || ctxs[i]->comm) return fail(ctxs[i], MPC_E_STATE, "mpc_comm_init_all: context %d is null or already has a communicator", i);
+  NcclApi* api = nccl_api();
+  if (!api->error.empty()) return fail(ctxs[0], MPC_E_STATE, "%s", api->error.c_str());
+  std::vector<ncclComm_t> comms((size_t)n);
+  std::vector<int> devs((size_t)n);
+  for (int i = 0; i < n; i++) devs[(size_t)i] = ctxs[i]->device;
+  {
+    StdoutToStderr quiet;
+    MPC_NCCL(ctxs[0], api, api->CommInitAll(comms.data(), n, devs.data()));
+  }
+  for (int i = 0; i < n; i++) {
+    ctxs[i]->comm = comms[(size_t)i];
+    ctxs[i]->comm_owned = true;
+    const int rc = ensure_reduced(ctxs[i]);
+    if (rc != MPC_OK) return rc;
+  }
+  return MPC_OK;
+}
+
+int mpc_attach_comm(mpc_ctx* ctx, void* nccl_comm) {
+  if (!ctx) return MPC_E_ARG;
+  if (ctx->comm && ctx->comm_owned) return fail(ctx, MPC_E_STATE, "mpc_attach_comm: the context owns a communicator already");
+  NcclApi* api = nccl_api();
+  if (!api->error.empty()) return fail(ctx, MPC_E_STATE, "%s", api->error.c_str());
+  ctx->comm = (ncclComm_t)nccl_comm;
+  ctx->comm_owned = false;
+  return nccl_comm ? ensure_reduced(ctx) : MPC_OK;
+}
+
+int mpc_allreduce_stats(mpc_ctx** ctxs, int n) {
+  if (!ctxs || n < 1) return fail(nullptr, MPC_E_ARG, "mpc_allreduce_stats: bad argument");
+  NcclApi* api = nullptr;
+  for (int i = 0; i < n; i++) {
+    mpc_ctx* ctx = ctxs[i];
+    if (!ctx) return fail(nullptr, MPC_E_ARG, "mpc_allreduce_stats: null context");
+    int rc = ensure_reduced(ctx);
+    if (rc != MPC_OK) return rc;
+    MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+    // chunks still in flight on the mpc_submit_host stage streams must land in d_stats before it is read
+    for (Stage& st : ctx->stage)
+      if (st.busy) MPC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st.done, 0));
+    MPC_CUDA(ctx, cudaMemcpyAsync(ctx->d_reduced, ctx->d_stats, mpc::kStatsWords * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->comm && !api) {
+      api = nccl_api();
+      if (!api->error.empty()) return fail(ctx, MPC_E_STATE, "%s", api->error.c_str());
+    }
+  }
+  if (!api) return MPC_OK;  // no communicator anywhere: one GPU, the copy is the reduction
+  MPC_NCCL(ctxs[0], api, api->GroupStart());
+  for (int i = 0; i < n; i++) {
+    mpc_ctx* ctx = ctxs[i];
+    if (!ctx->comm) { api->GroupEnd(); return fail(ctx, MPC_E_STATE, "mpc_allreduce_stats: context %d has no communicator", i); }
+    cudaSetDevice(ctx->device);
+    const ncclResult_t r = api->AllReduce(ctx->d_reduced, ctx->d_reduced, mpc::kStatsWords, ncclUint64, ncclSum, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) { api->GroupEnd(); return fail(ctx, MPC_E_CUDA, "ncclAllReduce failed: %s", api->GetErrorString(r)); }
+  }
+  MPC_NCCL(ctxs[0], api, api->GroupEnd());
+  return MPC_OK;
+}
+
+int mpc_reduced_stats(mpc_ctx* ctx, mpc_stats_pod* out) {
+  if (!ctx || !out) return MPC_E_ARG;
+  if (!ctx->d_reduced) return fail(ctx, MPC_E_STATE, "mpc_reduced_stats: no all-reduce has been issued on this context");
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<uint64_t> host(mpc::kStatsWords);
+  MPC_CUDA(ctx, cudaMemcpy(host.data(), ctx->d_reduced, mpc::kStatsWords * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return mpc_stats_expand(&ctx->cfg, host.data(), host.size(), out);
+}
+
+int mpc_reduced_device_ptr(mpc_ctx* ctx, uint64_t** d_reduced, size_t* n_words) {
+  if (!ctx || !d_reduced || !n_words) return MPC_E_ARG;
+  int rc = ensure_reduced(ctx);
+  if (rc != MPC_OK) return rc;
+  *d_reduced = ctx->d_reduced;
+  *n_words = mpc::kStatsWords;
+  return MPC_OK;
+}
+
+int mpc_finish_allreduce(mpc_ctx** ctxs, int n, mpc_stats_pod* out) {
+  if (!ctxs || n < 1 || !out) return fail(nullptr, MPC_E_ARG, "mpc_finish_allreduce: bad argument");
+  for (int i = 0; i < n; i++) {
+    int rc = mpc_sync(ctxs[i]);
+    if (rc != MPC_OK) return rc;
+  }
+  int rc = mpc_allreduce_stats(ctxs, n);
+  if (rc != MPC_OK) return rc;
+  for (int i = 1; i < n; i++) {
+    MPC_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+    MPC_CUDA(ctxs[i], cudaStreamSynchronize(ctxs[i]->stream));
+  }
+  return mpc_reduced_stats(ctxs[0], out);
 }
 
 int mpc_synth_device(mpc_ctx* ctx, uint8_t* d_lines, uint64_t first_block, uint64_t n_blocks, uint64_t total_blocks,

@@ -274,14 +274,11 @@ cudaError_t launch_generic(const GenericParams& params, const GenericModule* d_m
   const int K = params.num_modules + 1;
   size_t smem = sizeof(GenericModule) * (size_t)params.num_predcomp + sizeof(unsigned long long) * 2 * K +
                 sizeof(uint32_t) * (size_t)K * params.hist_bins + sizeof(WarpScratch) * kWarpsPerCta;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mpc_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  // the opt-in is a per-device (per-context) attribute: set it on every launch, as launch_spec does
+  cudaError_t e = cudaFuncSetAttribute(mpc_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_generic_kernel, kThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_generic_kernel, kThreads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (n_blocks + kWarpsPerCta - 1) / kWarpsPerCta;

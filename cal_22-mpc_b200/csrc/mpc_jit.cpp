@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <fstream>
 #include <mutex>
 
@@ -83,13 +84,19 @@ int jit_compile(const mpc_config_pod& cfg, std::vector<char>* cubin, SpecTraits*
   std::string cache_path;
   if (const char* dir = getenv("MPC_JIT_CACHE_DIR")) {
     char name[64];
+    int nv_major = 0, nv_minor = 0;
+    nvrtcVersion(&nv_major, &nv_minor);  // a cubin built by another compiler version is another entry
     snprintf(name, sizeof(name), "/mpc_b200_%016llx.cubin",
-             (unsigned long long)(fnv1a(src) ^ (fnv1a(kHdr_mpc_spec_cuh) * 3) ^ (fnv1a(kHdr_mpc_device_cuh) * 5)));
+             (unsigned long long)(fnv1a(src) ^ (fnv1a(kHdr_mpc_spec_cuh) * 3) ^ (fnv1a(kHdr_mpc_device_cuh) * 5) ^
+                                  (fnv1a(kHdr_mpc_layout_h) * 7) ^ ((uint64_t)(nv_major * 1000 + nv_minor) * 0x9E3779B97F4A7C15ull)));
     cache_path = std::string(dir) + name;
     std::ifstream in(cache_path, std::ios::binary);
     if (in) {
       cubin->assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
-      if (!cubin->empty()) return MPC_OK;
+      // entries are published with rename() (below), so a file that exists is complete; the ELF magic guards against
+      // anything else that may sit under this name
+      if (cubin->size() > 64 && memcmp(cubin->data(), "\x7f" "ELF", 4) == 0) return MPC_OK;
+      cubin->clear();
     }
   }
   const char* header_names[] = {"mpc_spec.cuh", "mpc_device.cuh", "mpc_layout.h"};
@@ -118,8 +125,15 @@ int jit_compile(const mpc_config_pod& cfg, std::vector<char>* cubin, SpecTraits*
   nvrtcGetCUBIN(prog, cubin->data());
   nvrtcDestroyProgram(&prog);
   if (!cache_path.empty()) {
-    std::ofstream out(cache_path, std::ios::binary);
-    out.write(cubin->data(), (std::streamsize)cubin->size());
+    // several ranks may build the same config at once: write to a private name, then publish atomically
+    const std::string tmp = cache_path + ".tmp." + std::to_string((long long)getpid());
+    bool ok = false;
+    {
+      std::ofstream out(tmp, std::ios::binary);
+      out.write(cubin->data(), (std::streamsize)cubin->size());
+      ok = out.good();
+    }
+    if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) remove(tmp.c_str());
   }
   return MPC_OK;
 }

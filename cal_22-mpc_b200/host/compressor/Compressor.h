@@ -17,8 +17,17 @@ class Compressor {
   std::string GetCompressorName() { return m_Stat->CompressorName; }
   // reference contract: compressed size of the line in bits incl. encoding bits; statistics updated
   virtual unsigned CompressLine(std::vector<uint8_t>& dataLine) = 0;
-  // batched form: nLines consecutive lines of GetCachelineSize() bytes; statistics updated, no per-line value
-  virtual void CompressBatch(const uint8_t* lines, uint64_t nLines) = 0;
+  // batched form: nLines consecutive lines of m_Stat->LineSize bytes; statistics updated, no per-line value.
+  // The default body is the reference's own per-line loop (main.cpp:237-243), so a compressor written against the
+  // reference interface (CompressLine only) compiles and runs unchanged; the GPU compressors override it.
+  virtual void CompressBatch(const uint8_t* lines, uint64_t nLines) {
+    const size_t L = m_Stat ? m_Stat->LineSize : 0;
+    std::vector<uint8_t> line(L);
+    for (uint64_t i = 0; i < nLines && L; i++) {
+      line.assign(lines + i * L, lines + (i + 1) * L);
+      CompressLine(line);
+    }
+  }
   virtual CompResult* GetResult() { return m_Stat; }
 
  protected:

@@ -1,11 +1,7 @@
 #include "VPC.h"
 
-#include <cuda_runtime.h>
-#include <nccl.h>
-
 #include <cstdio>
 #include <cstdlib>
-#include <unistd.h>
 #include <thread>
 
 namespace comp {
@@ -105,6 +101,8 @@ VPC::VPC(std::string configPath, int numGpus, int kernel) {
     if (kernel && mpc_set_kernel(c, kernel) != MPC_OK) die("mpc_set_kernel", c);
     m_Ctx.push_back(c);
   }
+  // communicators are created once per compressor, not per GetResult()
+  if (numGpus > 1 && mpc_comm_init_all(m_Ctx.data(), numGpus) != MPC_OK) die("mpc_comm_init_all", m_Ctx[0]);
   m_Stat = new VPCResult((unsigned)m_Cfg.line_size, m_Cfg.num_modules);
   m_Stat->CompressorName = "Contrastive Clustering Compressor";  // VPC.h:248
 }
@@ -151,43 +149,12 @@ void VPC::CompressBatch(const uint8_t* lines, uint64_t nLines) {
 }
 
 CompResult* VPC::GetResult() {
-  const int G = (int)m_Ctx.size();
-  if (G > 1) {
-    // one exchange for the whole run: ncclAllReduce(sum, uint64) of the statistics vectors over NVLink
-    std::vector<ncclComm_t> comms(G);
-    std::vector<int> devs(G);
-    for (int g = 0; g < G; g++) devs[g] = g;
-    // stdout carries exactly what the reference prints ("comp.ratio: ..."): whatever NCCL writes while it initialises (its
-    // version line under NCCL_DEBUG=VERSION, which this image sets, goes to stdout) is sent to stderr instead
-    fflush(stdout);
-    const int saved_stdout = dup(1);
-    dup2(2, 1);
-    const ncclResult_t init_rc = ncclCommInitAll(comms.data(), G, devs.data());
-    fflush(stdout);
-    dup2(saved_stdout, 1);
-    close(saved_stdout);
-    if (init_rc != ncclSuccess) { printf("ncclCommInitAll failed\n"); exit(1); }
-    for (int g = 0; g < G; g++) mpc_sync(m_Ctx[g]);
-    ncclGroupStart();
-    for (int g = 0; g < G; g++) {
-      uint64_t* p = nullptr;
-      size_t n = 0;
-      mpc_stats_device_ptr(m_Ctx[g], &p, &n);
-      cudaSetDevice(g);
-      ncclAllReduce(p, p, n, ncclUint64, ncclSum, comms[g], 0);
-    }
-    ncclGroupEnd();
-    for (int g = 0; g < G; g++) { cudaSetDevice(g); cudaStreamSynchronize(0); ncclCommDestroy(comms[g]); }
-  }
+  // one exchange for the whole run: the library all-reduces (sum, uint64) a copy of the statistics
+  // vectors over the communicators created in the constructor; with one GPU this is mpc_finish
   mpc_stats_pod* pod = new mpc_stats_pod;
-  if (mpc_finish(m_Ctx[0], pod) != MPC_OK) die("mpc_finish", m_Ctx[0]);
+  if (mpc_finish_allreduce(m_Ctx.data(), (int)m_Ctx.size(), pod) != MPC_OK) die("mpc_finish_allreduce", m_Ctx[0]);
   static_cast<VPCResult*>(m_Stat)->Fill(*pod);
   delete pod;
-  if (G > 1) {
-    // after the all-reduce every device holds the global vector; keep device 0's and clear the others so that
-    // a later batch does not count the sum G times
-    for (int g = 1; g < G; g++) mpc_reset(m_Ctx[g]);
-  }
   return m_Stat;
 }
 

@@ -4,6 +4,7 @@
 #ifndef MPCB_LOADER_H_
 #define MPCB_LOADER_H_
 
+#include <algorithm>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -36,7 +37,9 @@ struct MemReq_t {  // Loader.h:24-60
 class Loader {
  public:
   explicit Loader(const std::string& filePath) : m_FilePath(filePath) {}
-  virtual ~Loader() {}
+  virtual ~Loader() { delete m_ChunkReq; }
+  // the request object GetCacheline fills; the reference's driver picks the type per loader (main.cpp:210-215)
+  virtual MemReq_t* NewMemReq() { return new MemReq_t; }
   // reference interface (Loader.h:77-82)
   virtual MemReq_t* GetCacheline(MemReq_t*) = 0;
   virtual unsigned GetCachelineSize() = 0;
@@ -44,13 +47,30 @@ class Loader {
   virtual void Reset() = 0;
   // batched form: copies up to maxLines of the lines compressLines would still see (main.cpp:237-243)
   // into dst and returns how many were written; 0 = end of input.
-  virtual uint64_t GetChunk(uint8_t* dst, uint64_t maxLines) = 0;
+  // The default body is the reference's own loop over GetCacheline (main.cpp:229-243: a request flagged isEnd is
+  // not compressed), so a loader written against the reference interface compiles and runs unchanged.
+  virtual uint64_t GetChunk(uint8_t* dst, uint64_t maxLines) {
+    const size_t L = GetCachelineSize();
+    if (!m_ChunkReq) m_ChunkReq = NewMemReq();
+    uint64_t n = 0;
+    while (n < maxLines && !m_ChunkEnd) {
+      m_ChunkReq->Reset();
+      MemReq_t* r = GetCacheline(m_ChunkReq);
+      if (!r || r->isEnd) { m_ChunkEnd = true; break; }
+      if (r->data.size() != L) continue;  // not a line of the dump (the reference's driver filters these, main.cpp:222-224)
+      std::copy(r->data.begin(), r->data.end(), dst + n * L);
+      n++;
+    }
+    return n;
+  }
   // zero-copy form for loaders that hold the lines contiguously: pointer to the remaining lines, count
   // in *nLines, and the cursor moves to the end.  nullptr if unsupported.
   virtual const uint8_t* GetAll(uint64_t* nLines) { *nLines = 0; return nullptr; }
 
  protected:
   const std::string m_FilePath;
+  bool m_ChunkEnd = false;  // default GetChunk: the reference loop has seen isEnd
+  MemReq_t* m_ChunkReq = nullptr;
 };
 
 }  // namespace trace

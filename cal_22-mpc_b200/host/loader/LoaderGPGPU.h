@@ -53,6 +53,7 @@ class LoaderGPGPU : public Loader {
   void Reset() override;                              // LoaderGPGPU.cpp:73-79
   // payloads of the GLOBAL_ACC_R/W records (the lines compressLines keeps, main.cpp:216-227), densely packed
   uint64_t GetChunk(uint8_t* dst, uint64_t maxLines) override;
+  MemReq_t* NewMemReq() override { return new MemReqGPU_t; }
   const std::string& Error() const { return m_Error; }
 
  private:

@@ -73,7 +73,15 @@ int main(int argc, char** argv) {
 
   comp::Compressor* compressor = nullptr;
   if (algorithm == "VPC") {
-    compressor = new comp::VPC(configPath, gpus, kernel);  // main.cpp:88-91
+    comp::VPC* vpc = new comp::VPC(configPath, gpus, kernel);  // main.cpp:88-91
+    // The reference ignores the loader's line size for VPC and strides by the config's lineSize (VPC.cpp:101): with a
+    // mismatch it reads past the loader's buffer (undefined behaviour).  Refused here, like the other UB configs.
+    if ((unsigned)vpc->GetCachelineSize() != lineSize) {
+      printf("Line size mismatch: \"%s\" holds %u-byte lines, config \"%s\" has lineSize %d\n", tracePath.c_str(), lineSize,
+             configPath.c_str(), vpc->GetCachelineSize());
+      return 1;
+    }
+    compressor = vpc;
   } else if (algorithm == "BDI" || algorithm == "FPC" || algorithm == "BPC" || algorithm == "CPACK" || algorithm == "SC2") {
     compressor = new comp::VariantCompressor(algorithm, lineSize, loader->GetNumLines());  // main.cpp:92-116
   } else if (algorithm == "PATTERN") {

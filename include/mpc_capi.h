@@ -139,6 +139,30 @@ int mpc_finish(mpc_ctx* ctx, mpc_stats_pod* out);
 /* Expand a host copy of a statistics vector (e.g. after an allreduce done elsewhere). */
 int mpc_stats_expand(const mpc_config_pod* cfg, const uint64_t* words, size_t n_words, mpc_stats_pod* out);
 
+/* ---- multi-GPU: blocks are independent, so every GPU compresses a contiguous shard of the dump
+ * and the job's ONE exchange is an all-reduce (sum, uint64) of the statistics vector over NVLink.  The reference has no
+ * counterpart (single process, single thread; VPCResult::Update, VPC.h:49-76, is the state that is summed).
+ * One context per GPU.  Multi-process jobs (one rank per GPU): rank 0 calls mpc_comm_unique_id, ships the bytes to the
+ * other ranks by any means, every rank calls mpc_comm_init_rank.  Single-process jobs: mpc_comm_init_all over the
+ * process's contexts.  A caller that already has an ncclComm_t can lend it with mpc_attach_comm (not destroyed by
+ * mpc_destroy).  NCCL is loaded with dlopen on first use; every NCCL return code is checked and reported through
+ * mpc_last_error(). */
+#define MPC_COMM_UID_BYTES 128
+int mpc_comm_unique_id(void* uid, size_t uid_len);
+int mpc_comm_init_rank(mpc_ctx* ctx, const void* uid, size_t uid_len, int nranks, int rank);
+int mpc_comm_init_all(mpc_ctx** ctxs, int n);
+int mpc_attach_comm(mpc_ctx* ctx, void* nccl_comm);
+/* Asynchronous, on each context's stream: copy the statistics vector aside and all-reduce the copy over the
+ * communicator (ncclAllReduce, ncclUint64, ncclSum; one NCCL group over the n local contexts).  The local vector keeps
+ * accumulating, so the call can be repeated.  Contexts without a communicator (a one-GPU job): the copy is the result. */
+int mpc_allreduce_stats(mpc_ctx** ctxs, int n);
+/* Wait for the context's stream, copy the all-reduced vector back and expand it. */
+int mpc_reduced_stats(mpc_ctx* ctx, mpc_stats_pod* out);
+/* the all-reduced vector itself (MPC_STATS_WORDS uint64, device memory) */
+int mpc_reduced_device_ptr(mpc_ctx* ctx, uint64_t** d_reduced, size_t* n_words);
+/* mpc_sync on every context + mpc_allreduce_stats + mpc_reduced_stats(ctxs[0]): the multi-GPU form of mpc_finish(). */
+int mpc_finish_allreduce(mpc_ctx** ctxs, int n, mpc_stats_pod* out);
+
 /* Zero the device statistics (new file / new run). */
 int mpc_reset(mpc_ctx* ctx);
 

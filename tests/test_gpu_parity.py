@@ -248,3 +248,98 @@ def test_four_gib_mixed_properties(mpcb):
     sizes, sels = mpcb.unpack(packed[w0:w0 + wn].cpu().numpy().view(np.uint16))
     r = OracleMPC(cfg_path(cfg)).run(synth("mixed_hashed", 31337, w0, wn, n))
     assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
+
+
+def _full_dump_parity(mpcb, cfgs, kind, gib, seed, piece_mib=256):
+    """Every block of a BASELINE-size dump against the threaded CPU oracle: the dump is generated on the device, the
+    packed per-block results and the data come back in pieces, the oracle runs on each piece; totals, per-cluster counts,
+    histograms and MAE/MSE numerators of the whole dump must equal the oracle's sums."""
+    import torch
+    n = (gib << 30) // 128
+    d = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    packed = torch.zeros(n, dtype=torch.int16, device="cuda")
+    ms = {c: mpcb.Mpc(cfg_path(c)) for c in cfgs}
+    next(iter(ms.values())).synth_device(d.data_ptr(), 0, n, n, kind, seed)
+    next(iter(ms.values())).sync()
+    piece = (piece_mib << 20) // 128
+    host_pieces = None
+    for c, m in ms.items():
+        m.reset()
+        m.submit_device(d.data_ptr(), n, packed.data_ptr())
+        st = m.finish()
+        got = packed.cpu().numpy().view(np.uint16)
+        sizes, sels = mpcb.unpack(got)
+        orc = OracleMPC(cfg_path(c))
+        tot = None
+        mismatches = 0
+        for lo in range(0, n, piece):
+            hi = min(n, lo + piece)
+            blocks = d[lo * 128:hi * 128].cpu().numpy().reshape(-1, 128)
+            r = orc.run(blocks)
+            mismatches += int(np.count_nonzero((sizes[lo:hi] != r.sizes) | (sels[lo:hi] != r.sels)))
+            part = [r.blocks, r.OriginalSize, r.CompressedSize, r.count, r.comp_bits, r.res_lines, r.res_abs, r.res_sq, r.hist]
+            tot = part if tot is None else [a + b for a, b in zip(tot, part)]
+        assert mismatches == 0, f"{c}/{kind}: {mismatches} of {n} blocks differ from the oracle"
+        assert (st.blocks, st.OriginalSize, st.CompressedSize) == (tot[0], tot[1], tot[2])
+        assert np.array_equal(st.count, tot[3]) and np.array_equal(st.comp_bits, tot[4]) and np.array_equal(st.res_lines, tot[5])
+        assert np.array_equal(st.res_abs, tot[6]) and np.array_equal(st.res_sq, tot[7])
+        hb = tot[8].shape[1]
+        assert np.array_equal(st.hist[:, :hb], tot[8]) and not st.hist[:, hb:].any()
+    del host_pieces
+
+
+def test_full_1gib_smooth_every_block_equals_oracle(mpcb):
+    """BASELINE configs[1] (the headline workload), all 8 388 608 blocks."""
+    _full_dump_parity(mpcb, ["F4"], "smooth_f32", 1, 2024)
+
+
+def test_full_4gib_mixed_every_block_equals_oracle(mpcb):
+    """BASELINE configs[2] (4 GiB, every branch), all 33 554 432 blocks, column-major (F4) and plane-major (P6) kernels."""
+    _full_dump_parity(mpcb, ["F4", "P6"], "mixed_hashed", 4, 31337)
+
+
+def test_finish_allreduce_on_one_gpu(mpcb):
+    """The multi-GPU finish on a one-GPU job: without a communicator the all-reduce is the copy, and with a one-rank NCCL
+    communicator (mpc_comm_unique_id + mpc_comm_init_rank: NCCL resolved with dlopen, every return code checked) the
+    ncclAllReduce of the statistics vector must leave it unchanged; local statistics keep accumulating afterwards."""
+    blocks = synth("mixed_hashed", 11, 0, 50000, 50000)
+    r = OracleMPC(cfg_path("F4")).run(blocks)
+    m = mpcb.Mpc(cfg_path("F4"))
+    m.reset()
+    m.submit_host(blocks)
+    st = m.finish_allreduce()
+    assert st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count)
+    m.comm_init_rank(mpcb.Mpc.comm_unique_id(), 1, 0)
+    st = m.finish_allreduce()
+    assert st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count) and np.array_equal(st.res_sq, r.res_sq)
+    m.submit_host(blocks)
+    st = m.finish_allreduce()
+    assert st.CompressedSize == 2 * r.CompressedSize and np.array_equal(st.hist[:, :r.hist.shape[1]], 2 * r.hist)
+    with pytest.raises(mpcb.MpcError):
+        m.comm_init_rank(mpcb.Mpc.comm_unique_id(), 1, 0)  # a context has one communicator
+
+
+def test_two_gpu_shards_allreduce_equals_oracle(mpcb):
+    """SURVEY.md section 8e on hardware: two contexts on two GPUs, contiguous shards, mpc_comm_init_all +
+    mpc_finish_allreduce -- the reduced statistics equal the oracle's over the whole dump, per-block results per shard."""
+    import ctypes as C
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 400001
+    blocks = synth("mixed_hashed", 12, 0, n, n)
+    r = OracleMPC(cfg_path("P6")).run(blocks)
+    ms = [mpcb.Mpc(cfg_path("P6"), device=g) for g in range(2)]
+    arr = (C.c_void_p * 2)(*[m.h for m in ms])
+    assert mpcb.lib().mpc_comm_init_all(arr, 2) == 0, mpcb.lib().mpc_global_error()
+    per = (n + 1) // 2
+    packed = [np.zeros(per, np.uint16), np.zeros(n - per, np.uint16)]
+    ms[0].submit_host(blocks[:per], packed[0])
+    ms[1].submit_host(blocks[per:], packed[1])
+    pod = mpcb.capi.StatsPod()
+    assert mpcb.lib().mpc_finish_allreduce(arr, 2, C.byref(pod)) == 0, mpcb.lib().mpc_last_error(ms[0].h)
+    st = mpcb.capi.Stats(pod, ms[0].cfg.num_modules, 128)
+    sizes, sels = mpcb.unpack(np.concatenate(packed))
+    assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
+    assert st.blocks == n and st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count)
+    assert np.array_equal(st.res_abs, r.res_abs) and np.array_equal(st.hist[:, :r.hist.shape[1]], r.hist)

@@ -156,3 +156,51 @@ def test_multi_gpu_cli_equals_reference(tmp_path, golden):
     assert stdout == open(os.path.join(GOLD, "cli_F4_stdout.txt")).read()
     for suffix in ("results.csv", "results_detail.csv"):
         assert open(out / f"F4_{suffix}").read() == open(os.path.join(GOLD, f"cli_F4_{suffix}")).read(), suffix
+
+
+def test_reference_style_plugins_compile_and_run_unchanged(tmp_path):
+    """Compressor.h / Loader.h boundary: a compressor that only implements CompressLine and a loader that only implements
+    the four reference virtuals compile against the mirror headers; the default CompressBatch / GetChunk bodies are the
+    reference's per-line loops (main.cpp:229-244), including the dropped isEnd line."""
+    host = os.path.join(ROOT, "cal_22-mpc_b200", "host")
+    exe = str(tmp_path / "refstyle")
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I" + host, "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "ref_style_plugins.cpp"), os.path.join(host, "utils.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, check=True)
+    assert r.stdout.split() == ["9", str(9 * 32 * 8), str(sum(range(9)) * 32)]
+
+
+@pytest.mark.gpu
+def test_line_size_mismatch_is_refused(tmp_path):
+    """A [N,32] dump under a 128-byte config would be read out of bounds by the reference (VPC.cpp:101 ignores the loader's
+    line size): refused with a message and exit code 1."""
+    _build()
+    np.save(tmp_path / "d32.npy", np.zeros((64, 32), np.uint8))
+    r = subprocess.run([BIN, "-a", "VPC", "-i", str(tmp_path / "d32.npy"), "-c", cfg_path("P6"), "-o", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Line size mismatch" in r.stdout
+
+
+@pytest.mark.gpu
+def test_config1_survey_dump_through_bin_run(tmp_path):
+    """BASELINE configs[0]: `bin/run VPC <ds> <out> P6.json` over the survey's 64 MiB mixed dump (524 289 rows; BASELINE.md
+    section 3) must print the reference's `comp.ratio: 1.4392912514797536` and write the CSV bytes the unmodified reference
+    wrote for the same dump through its own bin/run (tests/golden/cli_survey_*, made by tests/golden/make_golden_survey.py)."""
+    import hashlib
+    import json
+    from tools.gen_dump import survey_mixed
+    _build()
+    meta = json.load(open(os.path.join(GOLD, "cli_survey.json")))
+    dump = survey_mixed(meta["rows"])
+    # the recipe draws from numpy's default_rng: the golden only applies to the same byte stream
+    assert hashlib.sha256(dump.tobytes()).hexdigest() == meta["sha256"], "numpy's random stream differs from the golden's"
+    ds, out = tmp_path / "ds", tmp_path / "out"
+    ds.mkdir()
+    out.mkdir()
+    np.save(ds / "survey_mixed.npy", dump)
+    r = subprocess.run([RUN, "VPC", str(ds), str(out), cfg_path("P6")], capture_output=True, text=True, cwd=os.path.join(ROOT, "bin"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "comp.ratio: 1.4392912514797536" in r.stdout
+    assert r.stdout == open(os.path.join(GOLD, "cli_survey_P6_stdout.txt")).read()
+    for suffix in ("results.csv", "results_detail.csv"):
+        assert open(out / f"P6_{suffix}").read() == open(os.path.join(GOLD, f"cli_survey_P6_{suffix}")).read(), suffix
