@@ -55,6 +55,11 @@ class PatternStats(C.Structure):
                         + list(self.symbol_counts_nontrivial), dtype=np.uint64)
 
 
+class Sc2Table(C.Structure):
+    """mpc_sc2_table (include/mpc_capi.h)"""
+    _fields_ = [("n", C.c_uint32), ("symbols", C.c_uint32 * 1024), ("lengths", C.c_uint8 * 1024)]
+
+
 class VariantStats(C.Structure):
     _fields_ = [("blocks", C.c_uint64), ("original_bits", C.c_uint64), ("compressed_bits", C.c_uint64),
                 ("counts", C.c_uint64 * 16)]
@@ -80,7 +85,7 @@ SYMBOLS = ["mpc_config_from_json_file", "mpc_config_from_json_text", "mpc_config
            "mpc_sc2_error", "mpc_cpack_run_host", "mpc_jit_compile_check", "mpc_enable_timing",
            "mpc_pattern_run_device", "mpc_pattern_run_host", "mpc_pattern_error",
            "mpc_comm_unique_id", "mpc_comm_init_rank", "mpc_comm_init_all", "mpc_attach_comm", "mpc_allreduce_stats",
-           "mpc_reduced_stats", "mpc_reduced_device_ptr", "mpc_finish_allreduce"]
+           "mpc_reduced_stats", "mpc_reduced_device_ptr", "mpc_finish_allreduce", "mpc_submit_file", "mpc_prepare_host", "mpc_sc2_build_table", "mpc_sc2_apply_device"]
 
 
 def lib():
@@ -108,6 +113,8 @@ def lib():
     l.mpc_kernel_name.restype = C.c_char_p
     l.mpc_submit_device.argtypes = [vp, vp, u64, vp]
     l.mpc_submit_host.argtypes = [vp, vp, u64, vp]
+    l.mpc_submit_file.argtypes = [vp, C.c_int, u64, u64, vp, C.c_int]
+    l.mpc_prepare_host.argtypes = [vp]
     l.mpc_sync.argtypes = [vp]
     l.mpc_stats_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     l.mpc_finish.argtypes = [vp, C.POINTER(StatsPod)]
@@ -122,6 +129,8 @@ def lib():
     l.mpc_sc2_run_device.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
     l.mpc_sc2_run_host.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
     l.mpc_sc2_error.restype = C.c_char_p
+    l.mpc_sc2_build_table.argtypes = [C.c_int, vp, u64, C.c_uint32, C.POINTER(Sc2Table)]
+    l.mpc_sc2_apply_device.argtypes = [C.c_int, vp, u64, u64, u64, C.c_uint32, C.POINTER(Sc2Table), vp, C.POINTER(VariantStats), C.POINTER(C.c_float)]
     l.mpc_cpack_run_host.argtypes = [vp, u64, C.c_uint32, vp, C.POINTER(VariantStats)]
     l.mpc_pattern_run_device.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(PatternStats), C.POINTER(C.c_float)]
     l.mpc_pattern_run_host.argtypes = [C.c_int, vp, u64, C.c_uint32, u64, vp, C.POINTER(PatternStats), C.POINTER(C.c_float)]
@@ -236,6 +245,11 @@ class Mpc:
 
     def submit_host_ptr(self, ptr, n_blocks, packed_ptr=None):
         self._check(lib().mpc_submit_host(self.h, ptr, n_blocks, packed_ptr))
+
+    def submit_file(self, fd, file_offset, n_blocks, packed=None, direct_io=False):
+        pp = packed.ctypes.data if packed is not None else None
+        self._keep = (packed,)
+        self._check(lib().mpc_submit_file(self.h, fd, file_offset, n_blocks, pp, 1 if direct_io else 0))
 
     def sync(self):
         self._check(lib().mpc_sync(self.h))

@@ -4,8 +4,10 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library resolves the NCCL entry points with dlopen when a communicator is first used
+#include <sys/stat.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -23,7 +25,10 @@ namespace {
 
 thread_local std::string g_error;
 
-struct Stage {             // one half of the double buffer used by mpc_submit_host
+constexpr int kHostStages = 3;  // pinned/device staging ring of mpc_submit_host / mpc_submit_file: fill, copy and compute overlap
+constexpr size_t kStagePad = 4096;  // room for the unaligned head of an O_DIRECT read
+
+struct Stage {             // one slot of the staging ring used by mpc_submit_host / mpc_submit_file
   cudaStream_t stream = nullptr;
   uint8_t* h_pinned = nullptr;
   uint8_t* d_lines = nullptr;
@@ -49,11 +54,11 @@ struct mpc_ctx {
   mpc::JitKernel* jit = nullptr;          // specialised kernel built at run time (NVRTC) when none is compiled in
   int kernel_choice = 0;
   uint64_t* d_stats = nullptr;
-  uint32_t* d_sched = nullptr;            // tile-scheduler words of the specialised kernels: 3 slots (device stream, 2 stages) x 32 words
+  uint32_t* d_sched = nullptr;            // tile-scheduler words of the specialised kernels: 1 + kHostStages slots (device stream, staging ring) x 32 words
   cudaStream_t own_stream = nullptr;      // created by mpc_create
   cudaStream_t stream = nullptr;          // stream used by mpc_submit_device / synth / stats (own or caller's)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_order = nullptr;
-  Stage stage[2];
+  Stage stage[kHostStages];
   uint64_t chunk_blocks = 0;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -157,16 +162,44 @@ void free_stages(mpc_ctx* ctx) {
   ctx->stages_ready = false;
 }
 
+// Page cache (or, with O_DIRECT, the device) -> pinned staging on several host threads: pread copies in the kernel without
+// the page faults of a mapping; one core moves ~5-10 GB/s, PCIe Gen5 wants ~55 GB/s.  Returns false on a short read / error.
+bool parallel_pread(int fd, uint8_t* dst, size_t bytes, uint64_t file_off, size_t align) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = hw >= 16 ? 12 : (hw >= 8 ? 6 : (hw >= 4 ? 3 : 1));
+  if (bytes < (8u << 20)) nt = 1;
+  size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+  if (per < align) per = align;
+  std::vector<std::thread> th;
+  std::vector<int> ok(nt, 1);
+  for (size_t t = 0; t < nt; t++) {
+    const size_t lo = t * per, hi = (lo + per < bytes) ? lo + per : bytes;
+    if (lo >= bytes) break;
+    auto work = [=, &ok]() {
+      size_t done = lo;
+      while (done < hi) {
+        const ssize_t r = pread(fd, dst + done, hi - done, (off_t)(file_off + done));
+        if (r <= 0) { ok[t] = 0; return; }
+        done += (size_t)r;
+      }
+    };
+    if (nt == 1) work(); else th.emplace_back(work);
+  }
+  for (auto& t : th) t.join();
+  for (int v : ok) if (!v) return false;
+  return true;
+}
+
 int ensure_stages(mpc_ctx* ctx) {
   if (ctx->stages_ready) return MPC_OK;
   free_stages(ctx);  // a previous attempt may have failed half way: start from nothing
-  ctx->chunk_blocks = (64ull << 20) / (uint64_t)ctx->cfg.line_size;  // 64 MiB per chunk
+  ctx->chunk_blocks = (32ull << 20) / (uint64_t)ctx->cfg.line_size;  // 32 MiB per chunk: full PCIe rate, short pipeline fill and drain
   const size_t bytes = (size_t)ctx->chunk_blocks * ctx->cfg.line_size;
   auto alloc = [&]() -> cudaError_t {
     cudaError_t e;
     for (Stage& st : ctx->stage) {
       if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
-      if ((e = cudaMallocHost(&st.h_pinned, bytes)) != cudaSuccess) return e;
+      if ((e = cudaMallocHost(&st.h_pinned, bytes + kStagePad)) != cudaSuccess) return e;
       if ((e = cudaMalloc(&st.d_lines, bytes)) != cudaSuccess) return e;
       if ((e = cudaMalloc(&st.d_packed, ctx->chunk_blocks * sizeof(uint16_t))) != cudaSuccess) return e;
       if ((e = cudaMallocHost(&st.h_packed, ctx->chunk_blocks * sizeof(uint16_t))) != cudaSuccess) return e;
@@ -287,8 +320,8 @@ int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out) {
   MPC_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
   MPC_CREATE_CUDA(cudaMalloc(&ctx->d_stats, mpc::kStatsWords * sizeof(uint64_t)));
   MPC_CREATE_CUDA(cudaMemsetAsync(ctx->d_stats, 0, mpc::kStatsWords * sizeof(uint64_t), ctx->stream));
-  MPC_CREATE_CUDA(cudaMalloc(&ctx->d_sched, 3 * 32 * sizeof(uint32_t)));
-  MPC_CREATE_CUDA(cudaMemsetAsync(ctx->d_sched, 0, 3 * 32 * sizeof(uint32_t), ctx->stream));
+  MPC_CREATE_CUDA(cudaMalloc(&ctx->d_sched, (1 + kHostStages) * 32 * sizeof(uint32_t)));
+  MPC_CREATE_CUDA(cudaMemsetAsync(ctx->d_sched, 0, (1 + kHostStages) * 32 * sizeof(uint32_t), ctx->stream));
   std::vector<mpc::GenericModule> gm((size_t)MPC_MAX_MODULES);
   mpc::build_generic_tables(ctx->cfg, &ctx->gparams, gm.data());
   const size_t gbytes = sizeof(mpc::GenericModule) * (size_t)(ctx->gparams.num_predcomp > 0 ? ctx->gparams.num_predcomp : 1);
@@ -439,9 +472,75 @@ int mpc_submit_host(mpc_ctx* ctx, const uint8_t* h_lines, uint64_t n_blocks, uin
     MPC_CUDA(ctx, cudaEventRecord(st.done, st.stream));
     st.busy = true;
     done_blocks += nb;
-    which ^= 1;
+    which = (which + 1) % kHostStages;
   }
   return MPC_OK;
+}
+
+int mpc_submit_file(mpc_ctx* ctx, int fd, uint64_t file_offset, uint64_t n_blocks, uint16_t* h_packed, int direct_io) {
+  if (!ctx) return MPC_E_ARG;
+  if (fd < 0) return fail(ctx, MPC_E_ARG, "mpc_submit_file: bad file descriptor");
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_stages(ctx);
+  if (rc != MPC_OK) return rc;
+  MPC_CUDA(ctx, cudaEventRecord(ctx->ev_order, ctx->stream));
+  for (Stage& st : ctx->stage) MPC_CUDA(ctx, cudaStreamWaitEvent(st.stream, ctx->ev_order, 0));
+  ctx->last_timing_pending = false;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  const uint64_t L = (uint64_t)ctx->cfg.line_size;
+  uint64_t done_blocks = 0;
+  int which = 0;
+  const bool trace = getenv("MPC_TRACE_IO") != nullptr;  // stderr: where the host thread's time goes
+  double t_read = 0, t_wait = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  while (done_blocks < n_blocks) {
+    Stage& st = ctx->stage[which];
+    const double tw0 = now();
+    rc = drain_stage(ctx, st);
+    if (rc != MPC_OK) return rc;
+    t_wait += now() - tw0;
+    const uint64_t nb = (n_blocks - done_blocks < ctx->chunk_blocks) ? (n_blocks - done_blocks) : ctx->chunk_blocks;
+    const uint64_t off = file_offset + done_blocks * L;
+    const double tr0 = now();
+    // O_DIRECT wants file offset, length and buffer aligned: read from the aligned offset below `off` (the stage has the room)
+    // and copy to the device from where the chunk's first byte landed
+    const uint64_t head = direct_io ? (off & (kStagePad - 1)) : 0;
+    size_t want = (size_t)(nb * L + head);
+    if (direct_io) want = (want + kStagePad - 1) & ~(kStagePad - 1);
+    // the tail of the last chunk may reach past the end of the file: a short read there is not an error
+    if (!parallel_pread(fd, st.h_pinned, want, off - head, direct_io ? kStagePad : 1)) {
+      struct stat sb;
+      if (fstat(fd, &sb) != 0 || (uint64_t)sb.st_size < off + nb * L)
+        return fail(ctx, MPC_E_IO, "mpc_submit_file: short read at offset %llu", (unsigned long long)off);
+    }
+    t_read += now() - tr0;
+    MPC_CUDA(ctx, cudaMemcpyAsync(st.d_lines, st.h_pinned + head, nb * L, cudaMemcpyHostToDevice, st.stream));
+    MPC_CUDA(ctx, cudaEventRecord(st.k_start, st.stream));
+    rc = launch(ctx, st.d_lines, nb, h_packed ? st.d_packed : nullptr, st.stream, 1 + which);
+    if (rc != MPC_OK) return rc;
+    MPC_CUDA(ctx, cudaEventRecord(st.k_stop, st.stream));
+    ctx->last_launches++;
+    if (h_packed) {
+      MPC_CUDA(ctx, cudaMemcpyAsync(st.h_packed, st.d_packed, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, st.stream));
+      st.user_packed = h_packed + done_blocks;
+      st.user_count = nb;
+    }
+    MPC_CUDA(ctx, cudaEventRecord(st.done, st.stream));
+    st.busy = true;
+    done_blocks += nb;
+    which = (which + 1) % kHostStages;
+  }
+  if (trace)
+    fprintf(stderr, "mpc_submit_file: %.1f MiB, pread %.1f ms (%.1f GB/s), waiting for a free slot %.1f ms\n", n_blocks * L / 1048576.0,
+            1e3 * t_read, t_read > 0 ? n_blocks * L / t_read / 1e9 : 0.0, 1e3 * t_wait);
+  return MPC_OK;
+}
+
+int mpc_prepare_host(mpc_ctx* ctx) {
+  if (!ctx) return MPC_E_ARG;
+  MPC_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ensure_stages(ctx);
 }
 
 int mpc_sync(mpc_ctx* ctx) {
@@ -505,7 +604,7 @@ int mpc_reset(mpc_ctx* ctx) {
   int rc = mpc_sync(ctx);
   if (rc != MPC_OK) return rc;
   MPC_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, mpc::kStatsWords * sizeof(uint64_t), ctx->stream));
-  MPC_CUDA(ctx, cudaMemsetAsync(ctx->d_sched, 0, 3 * 32 * sizeof(uint32_t), ctx->stream));
+  MPC_CUDA(ctx, cudaMemsetAsync(ctx->d_sched, 0, (1 + kHostStages) * 32 * sizeof(uint32_t), ctx->stream));
   MPC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MPC_OK;
 }

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -41,36 +42,38 @@ __global__ void pack_count_symbol(const uint32_t* __restrict__ sym, const uint32
   if (i < n) key[i] = ((uint64_t)cnt[i] << 32) | sym[i];
 }
 
+// Code table for the lookup kernel: open addressing, 4096 slots for <= 1024 symbols (load <= 25 %, ~1.2 probes per word),
+// built on the host from the (symbol, length) list.  s_len holds length + 1 (a single-symbol tree has length 0), 0 = empty.
+constexpr int kHashSlots = 4096;
+__host__ __device__ __forceinline__ uint32_t sc2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> 20; }
+
 __global__ void __launch_bounds__(kThreads)
-sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t sampling, const uint32_t* __restrict__ g_syms,
-                  const uint8_t* __restrict__ g_lens, int k, uint16_t* __restrict__ sizes, unsigned long long* __restrict__ total) {
+sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t first_block, uint64_t sampling, const uint32_t* __restrict__ g_keys,
+                  const uint8_t* __restrict__ g_lens, uint16_t* __restrict__ sizes, unsigned long long* __restrict__ total) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* s_stage = reinterpret_cast<uint4*>(smem_raw);
-  __shared__ uint32_t s_syms[1024];
-  __shared__ uint8_t s_lens[1024];
-  for (int i = threadIdx.x; i < 1024; i += kThreads) {
-    s_syms[i] = i < k ? g_syms[i] : 0xffffffffu;
-    s_lens[i] = i < k ? g_lens[i] : 33;
-  }
+  __shared__ uint32_t s_key[kHashSlots];
+  __shared__ uint8_t s_len[kHashSlots];
+  for (int i = threadIdx.x; i < kHashSlots; i += kThreads) { s_key[i] = g_keys[i]; s_len[i] = g_lens[i]; }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long bits = 0;
   tile::for_each_block(lines, n_blocks, s_stage + warp * tile::kStages * 256, kWarps,
                        [&](const uint32_t (&x)[32], uint64_t blk, bool valid) {
     uint32_t size = 0;
-    if (blk < sampling) {
+    if (first_block + blk < sampling) {
       size = 33u * 32u;  // sampling phase: every word is a miss (SC2.cpp:315-323 with an empty code map)
     } else {
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < 32; j++) {
         const uint32_t v = x[j];
-        int lo = 0, hi = k - 1;
-        uint32_t len = 33;
-        while (lo <= hi) {
-          const int mid = (lo + hi) >> 1;
-          const uint32_t s = s_syms[mid];
-          if (s == v) { len = s_lens[mid]; break; }
-          if (s < v) lo = mid + 1; else hi = mid - 1;
+        uint32_t idx = sc2_hash(v);
+        uint32_t len = 33u;
+        while (true) {
+          const uint32_t l = s_len[idx];
+          if (l == 0u) break;                                  // empty slot: not in the table
+          if (s_key[idx] == v) { len = l - 1u; break; }
+          idx = (idx + 1u) & (kHashSlots - 1);
         }
         size += len;
       }
@@ -145,86 +148,147 @@ void sc2_code_lengths(const std::vector<std::pair<uint32_t, uint64_t>>& sf, std:
 
 extern "C" const char* mpc_sc2_error(void) { return mpc::g_err.c_str(); }
 
-extern "C" int mpc_sc2_run_device(int device, const uint8_t* d_lines, uint64_t n_blocks, uint32_t line_size, uint64_t sampling_lines,
-                                  uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms) {
+namespace mpc {
+namespace {
+
+// Per-device workspace, kept for the life of the process: the sort buffers of the sampling phase (grown on demand), the code
+// table, the counters and the two timing events -- no allocation or event creation per call.
+struct Sc2Workspace {
+  int device = -1;
+  size_t words = 0, temp_bytes = 0, keys = 0;
+  uint32_t *d_sorted = nullptr, *d_unique = nullptr, *d_counts = nullptr;
+  int* d_runs = nullptr;
+  uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;
+  void* d_temp = nullptr;
+  uint32_t* d_tab_keys = nullptr;
+  uint8_t* d_tab_lens = nullptr;
+  unsigned long long* d_total = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+std::mutex g_ws_mutex;
+Sc2Workspace g_ws[16];
+
+int ws_get(int device, Sc2Workspace** out) {
+  if (device < 0 || device >= 16) return fail(MPC_E_ARG, "device index out of range");
+  Sc2Workspace& w = g_ws[device];
+  if (w.device != device) {
+    SC2_CUDA(cudaMalloc(&w.d_runs, sizeof(int)));
+    SC2_CUDA(cudaMalloc(&w.d_tab_keys, kHashSlots * 4));
+    SC2_CUDA(cudaMalloc(&w.d_tab_lens, kHashSlots));
+    SC2_CUDA(cudaMalloc(&w.d_total, 8));
+    SC2_CUDA(cudaEventCreate(&w.e0));
+    SC2_CUDA(cudaEventCreate(&w.e1));
+    w.device = device;
+  }
+  *out = &w;
+  return MPC_OK;
+}
+
+int ws_reserve(Sc2Workspace& w, size_t words) {
+  if (words <= w.words) return MPC_OK;
+  if (w.d_sorted) { cudaFree(w.d_sorted); cudaFree(w.d_unique); cudaFree(w.d_counts); cudaFree(w.d_temp); }
+  if (w.d_keys) { cudaFree(w.d_keys); cudaFree(w.d_keys_sorted); }
+  w.d_sorted = w.d_unique = w.d_counts = nullptr;
+  w.d_keys = w.d_keys_sorted = nullptr;
+  w.d_temp = nullptr;
+  w.words = 0;
+  SC2_CUDA(cudaMalloc(&w.d_sorted, words * 4));
+  SC2_CUDA(cudaMalloc(&w.d_unique, words * 4));
+  SC2_CUDA(cudaMalloc(&w.d_counts, words * 4));
+  SC2_CUDA(cudaMalloc(&w.d_keys, words * 8));
+  SC2_CUDA(cudaMalloc(&w.d_keys_sorted, words * 8));
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  const int nw = (int)words;
+  cub::DeviceRadixSort::SortKeys(nullptr, t1, w.d_sorted, w.d_sorted, nw);
+  cub::DeviceRunLengthEncode::Encode(nullptr, t2, w.d_sorted, w.d_unique, w.d_counts, w.d_runs, nw);
+  cub::DeviceRadixSort::SortKeys(nullptr, t3, w.d_keys, w.d_keys_sorted, nw);
+  w.temp_bytes = std::max(t1, std::max(t2, t3));
+  SC2_CUDA(cudaMalloc(&w.d_temp, w.temp_bytes));
+  w.words = words;
+  return MPC_OK;
+}
+
+}  // namespace
+}  // namespace mpc
+
+// Phase 1 (SC2.cpp:285-313): the code table from the first sampling_lines lines, which must be resident at d_lines.
+extern "C" int mpc_sc2_build_table(int device, const uint8_t* d_lines, uint64_t sampling_lines, uint32_t line_size, mpc_sc2_table* table) {
   using namespace mpc;
-  if (!out || (n_blocks && !d_lines)) return fail(MPC_E_ARG, "null argument");
+  if (!table || (sampling_lines && !d_lines)) return fail(MPC_E_ARG, "null argument");
   if (line_size != 128) return fail(MPC_E_ARG, "the GPU variants are built for 128-byte blocks");
-  if ((uintptr_t)d_lines & 15) return fail(MPC_E_ARG, "lines must be 16-byte aligned");
+  memset(table, 0, sizeof(*table));
+  if (sampling_lines == 0) return MPC_OK;
+  const uint64_t nw64 = sampling_lines * 32ull;
+  if (nw64 > 0x7fffffffull) return fail(MPC_E_ARG, "sampling window too large");
+  const int nw = (int)nw64;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
   SC2_CUDA(cudaSetDevice(device));
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaEvent_t e0, e1;
-  SC2_CUDA(cudaEventCreate(&e0));
-  SC2_CUDA(cudaEventCreate(&e1));
-  SC2_CUDA(cudaEventRecord(e0, 0));
+  Sc2Workspace* wp = nullptr;
+  int rc = ws_get(device, &wp);
+  if (rc != MPC_OK) return rc;
+  Sc2Workspace& w = *wp;
+  if ((rc = ws_reserve(w, (size_t)nw)) != MPC_OK) return rc;
+  // histogram of the sampled words = sort + run-length encode
+  const uint32_t* d_words = reinterpret_cast<const uint32_t*>(d_lines);
+  size_t t = w.temp_bytes;
+  SC2_CUDA(cub::DeviceRadixSort::SortKeys(w.d_temp, t, d_words, w.d_sorted, nw));
+  t = w.temp_bytes;
+  SC2_CUDA(cub::DeviceRunLengthEncode::Encode(w.d_temp, t, w.d_sorted, w.d_unique, w.d_counts, w.d_runs, nw));
+  int runs = 0;
+  SC2_CUDA(cudaMemcpy(&runs, w.d_runs, sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<uint32_t, uint64_t>> sf;
+  if (runs > 1024) {
+    // keep the 1024 largest by (count, symbol): the reference erases in ascending (freq, symbol) order (SC2.cpp:294-307)
+    pack_count_symbol<<<(runs + 255) / 256, 256>>>(w.d_unique, w.d_counts, w.d_keys, (uint32_t)runs);
+    t = w.temp_bytes;
+    SC2_CUDA(cub::DeviceRadixSort::SortKeys(w.d_temp, t, w.d_keys, w.d_keys_sorted, runs));
+    std::vector<uint64_t> top(1024);
+    SC2_CUDA(cudaMemcpy(top.data(), w.d_keys_sorted + (runs - 1024), 1024 * 8, cudaMemcpyDeviceToHost));
+    for (uint64_t k : top) sf.emplace_back((uint32_t)k, k >> 32);
+  } else {
+    std::vector<uint32_t> u((size_t)runs), c((size_t)runs);
+    SC2_CUDA(cudaMemcpy(u.data(), w.d_unique, (size_t)runs * 4, cudaMemcpyDeviceToHost));
+    SC2_CUDA(cudaMemcpy(c.data(), w.d_counts, (size_t)runs * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < runs; i++) sf.emplace_back(u[(size_t)i], c[(size_t)i]);
+  }
+  std::sort(sf.begin(), sf.end());  // ascending symbol = std::map iteration order
   std::vector<uint32_t> syms;
   std::vector<uint8_t> lens;
-  if (n_blocks > sampling_lines && sampling_lines > 0) {
-    // ---- phase 1: histogram of the sampled words = sort + run-length encode ----
-    const uint64_t nw64 = sampling_lines * 32ull;
-    if (nw64 > 0x7fffffffull) return fail(MPC_E_ARG, "sampling window too large");
-    const int nw = (int)nw64;
-    uint32_t *d_sorted = nullptr, *d_unique = nullptr, *d_counts = nullptr;
-    int* d_runs = nullptr;
-    uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;
-    void* d_temp = nullptr;
-    size_t temp1 = 0, temp2 = 0, temp3 = 0;
-    SC2_CUDA(cudaMalloc(&d_sorted, (size_t)nw * 4));
-    SC2_CUDA(cudaMalloc(&d_unique, (size_t)nw * 4));
-    SC2_CUDA(cudaMalloc(&d_counts, (size_t)nw * 4));
-    SC2_CUDA(cudaMalloc(&d_runs, sizeof(int)));
-    const uint32_t* d_words = reinterpret_cast<const uint32_t*>(d_lines);
-    cub::DeviceRadixSort::SortKeys(nullptr, temp1, d_words, d_sorted, nw);
-    cub::DeviceRunLengthEncode::Encode(nullptr, temp2, d_sorted, d_unique, d_counts, d_runs, nw);
-    cub::DeviceRadixSort::SortKeys(nullptr, temp3, d_keys, d_keys_sorted, nw);
-    const size_t temp = std::max(temp1, std::max(temp2, temp3));
-    SC2_CUDA(cudaMalloc(&d_temp, temp));
-    size_t t = temp;
-    SC2_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, t, d_words, d_sorted, nw));
-    t = temp;
-    SC2_CUDA(cub::DeviceRunLengthEncode::Encode(d_temp, t, d_sorted, d_unique, d_counts, d_runs, nw));
-    int runs = 0;
-    SC2_CUDA(cudaMemcpy(&runs, d_runs, sizeof(int), cudaMemcpyDeviceToHost));
-    std::vector<std::pair<uint32_t, uint64_t>> sf;
-    if (runs > 1024) {
-      // keep the 1024 largest by (count, symbol): the reference erases in ascending (freq, symbol) order (SC2.cpp:294-307)
-      SC2_CUDA(cudaMalloc(&d_keys, (size_t)runs * 8));
-      SC2_CUDA(cudaMalloc(&d_keys_sorted, (size_t)runs * 8));
-      pack_count_symbol<<<(runs + 255) / 256, 256>>>(d_unique, d_counts, d_keys, (uint32_t)runs);
-      t = temp;
-      SC2_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, t, d_keys, d_keys_sorted, runs));
-      std::vector<uint64_t> top(1024);
-      SC2_CUDA(cudaMemcpy(top.data(), d_keys_sorted + (runs - 1024), 1024 * 8, cudaMemcpyDeviceToHost));
-      for (uint64_t k : top) sf.emplace_back((uint32_t)k, k >> 32);
-      cudaFree(d_keys);
-      cudaFree(d_keys_sorted);
-    } else {
-      std::vector<uint32_t> u(runs), c(runs);
-      SC2_CUDA(cudaMemcpy(u.data(), d_unique, (size_t)runs * 4, cudaMemcpyDeviceToHost));
-      SC2_CUDA(cudaMemcpy(c.data(), d_counts, (size_t)runs * 4, cudaMemcpyDeviceToHost));
-      for (int i = 0; i < runs; i++) sf.emplace_back(u[i], c[i]);
-    }
-    cudaFree(d_temp);
-    cudaFree(d_sorted);
-    cudaFree(d_unique);
-    cudaFree(d_counts);
-    cudaFree(d_runs);
-    std::sort(sf.begin(), sf.end());  // ascending symbol = std::map iteration order
-    sc2_code_lengths(sf, &syms, &lens);
+  sc2_code_lengths(sf, &syms, &lens);
+  table->n = (uint32_t)syms.size();
+  for (size_t i = 0; i < syms.size(); i++) { table->symbols[i] = syms[i]; table->lengths[i] = lens[i]; }
+  return MPC_OK;
+}
+
+// Phase 2 (SC2.cpp:315-330): n_blocks lines whose first one is line `first_block` of the dump (a shard of it, or all of it):
+// lines below sampling_lines cost 33 bits per word, the others the code length of each word or 33.
+extern "C" int mpc_sc2_apply_device(int device, const uint8_t* d_lines, uint64_t n_blocks, uint64_t first_block, uint64_t sampling_lines,
+                                    uint32_t line_size, const mpc_sc2_table* table, uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms) {
+  using namespace mpc;
+  if (!out || !table || (n_blocks && !d_lines)) return fail(MPC_E_ARG, "null argument");
+  if (line_size != 128) return fail(MPC_E_ARG, "the GPU variants are built for 128-byte blocks");
+  if ((uintptr_t)d_lines & 15) return fail(MPC_E_ARG, "lines must be 16-byte aligned");
+  if (table->n > 1024) return fail(MPC_E_ARG, "code table holds more than 1024 symbols");
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  SC2_CUDA(cudaSetDevice(device));
+  Sc2Workspace* wp = nullptr;
+  int rc = ws_get(device, &wp);
+  if (rc != MPC_OK) return rc;
+  Sc2Workspace& w = *wp;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  std::vector<uint32_t> keys(kHashSlots, 0u);
+  std::vector<uint8_t> lens(kHashSlots, 0);
+  for (uint32_t i = 0; i < table->n; i++) {
+    uint32_t idx = sc2_hash(table->symbols[i]);
+    while (lens[idx]) idx = (idx + 1u) & (kHashSlots - 1);
+    keys[idx] = table->symbols[i];
+    lens[idx] = (uint8_t)(table->lengths[i] + 1);
   }
-  // ---- phase 2: per-block lookup ----
-  uint32_t* d_syms = nullptr;
-  uint8_t* d_lens = nullptr;
-  unsigned long long* d_total = nullptr;
-  SC2_CUDA(cudaMalloc(&d_syms, 1024 * 4));
-  SC2_CUDA(cudaMalloc(&d_lens, 1024));
-  SC2_CUDA(cudaMalloc(&d_total, 8));
-  SC2_CUDA(cudaMemset(d_total, 0, 8));
-  if (!syms.empty()) {
-    SC2_CUDA(cudaMemcpy(d_syms, syms.data(), syms.size() * 4, cudaMemcpyHostToDevice));
-    SC2_CUDA(cudaMemcpy(d_lens, lens.data(), lens.size(), cudaMemcpyHostToDevice));
-  }
+  SC2_CUDA(cudaEventRecord(w.e0, 0));
+  SC2_CUDA(cudaMemcpyAsync(w.d_tab_keys, keys.data(), kHashSlots * 4, cudaMemcpyHostToDevice, 0));
+  SC2_CUDA(cudaMemcpyAsync(w.d_tab_lens, lens.data(), kHashSlots, cudaMemcpyHostToDevice, 0));
+  SC2_CUDA(cudaMemsetAsync(w.d_total, 0, 8, 0));
   if (n_blocks) {
     const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
     SC2_CUDA(cudaFuncSetAttribute(sc2_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -232,48 +296,93 @@ extern "C" int mpc_sc2_run_device(int device, const uint8_t* d_lines, uint64_t n
     SC2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc2_lookup_kernel, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const uint64_t tiles = (n_blocks + 31) / 32;
-    uint64_t grid = std::min<uint64_t>((uint64_t)sms * per_sm, (tiles + kWarps - 1) / kWarps);
-    // lines [0, S) are sampling lines; when the dump has no more than S lines the tree is never built (SC2.cpp:285-313)
-    const uint64_t s_eff = (n_blocks > sampling_lines) ? sampling_lines : n_blocks;
-    sc2_lookup_kernel<<<(unsigned)grid, kThreads, smem>>>(reinterpret_cast<const uint4*>(d_lines), n_blocks, s_eff, d_syms, d_lens,
-                                                          (int)syms.size(), d_sizes, d_total);
+    const uint64_t grid = std::min<uint64_t>((uint64_t)sms * per_sm, (tiles + kWarps - 1) / kWarps);
+    sc2_lookup_kernel<<<(unsigned)grid, kThreads, smem>>>(reinterpret_cast<const uint4*>(d_lines), n_blocks, first_block, sampling_lines,
+                                                          w.d_tab_keys, w.d_tab_lens, d_sizes, w.d_total);
     SC2_CUDA(cudaGetLastError());
   }
-  SC2_CUDA(cudaEventRecord(e1, 0));
+  SC2_CUDA(cudaEventRecord(w.e1, 0));
   unsigned long long total = 0;
-  SC2_CUDA(cudaMemcpy(&total, d_total, 8, cudaMemcpyDeviceToHost));
+  SC2_CUDA(cudaMemcpy(&total, w.d_total, 8, cudaMemcpyDeviceToHost));
   float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d_syms);
-  cudaFree(d_lens);
-  cudaFree(d_total);
+  SC2_CUDA(cudaEventElapsedTime(&ms, w.e0, w.e1));
   memset(out, 0, sizeof(*out));
   out->blocks = n_blocks;
   out->original_bits = n_blocks * 8ull * line_size;
   out->compressed_bits = total;
-  out->counts[0] = syms.size();  // symbols that received a code
+  out->counts[0] = table->n;  // symbols that received a code
   if (kernel_ms) *kernel_ms = ms;
   return MPC_OK;
 }
 
+extern "C" int mpc_sc2_run_device(int device, const uint8_t* d_lines, uint64_t n_blocks, uint32_t line_size, uint64_t sampling_lines,
+                                  uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms) {
+  using namespace mpc;
+  if (!out || (n_blocks && !d_lines)) return fail(MPC_E_ARG, "null argument");
+  mpc_sc2_table table;
+  memset(&table, 0, sizeof(table));
+  cudaEvent_t t0 = nullptr, t1 = nullptr;  // the whole call on the device's clock: table build (sorts, host tree) + lookup
+  SC2_CUDA(cudaSetDevice(device));
+  SC2_CUDA(cudaEventCreateWithFlags(&t0, cudaEventDefault));
+  SC2_CUDA(cudaEventCreateWithFlags(&t1, cudaEventDefault));
+  cudaEventRecord(t0, 0);
+  int rc = MPC_OK;
+  // when the dump has no more than S lines the tree is never built (SC2.cpp:285-313): every line is a sampling line
+  if (n_blocks > sampling_lines && sampling_lines > 0) rc = mpc_sc2_build_table(device, d_lines, sampling_lines, line_size, &table);
+  float ms_apply = 0;
+  if (rc == MPC_OK) rc = mpc_sc2_apply_device(device, d_lines, n_blocks, 0, sampling_lines, line_size, &table, d_sizes, out, &ms_apply);
+  cudaEventRecord(t1, 0);
+  cudaEventSynchronize(t1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  if (rc == MPC_OK && kernel_ms) *kernel_ms = ms;
+  return rc;
+}
+
+// Host dump: the sampling window (at most 10^6 lines = 128 MB) goes to the device first for the table, then the dump streams
+// through two device buffers in chunks -- dumps larger than HBM work, every copy's return code is checked.
 extern "C" int mpc_sc2_run_host(int device, const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size, uint64_t sampling_lines,
                                 uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms) {
   using namespace mpc;
-  if (n_blocks && !h_lines) return fail(MPC_E_ARG, "null lines");
+  if (!out || (n_blocks && !h_lines)) return fail(MPC_E_ARG, "null argument");
+  if (line_size != 128) return fail(MPC_E_ARG, "the GPU variants are built for 128-byte blocks");
   SC2_CUDA(cudaSetDevice(device));
+  const uint64_t chunk = (256ull << 20) / line_size;
+  const bool build = n_blocks > sampling_lines && sampling_lines > 0;
+  const uint64_t cap = std::max<uint64_t>(std::min<uint64_t>(chunk, n_blocks ? n_blocks : 1), build ? sampling_lines : 1);
   uint8_t* d_lines = nullptr;
   uint16_t* d_sizes = nullptr;
-  const size_t bytes = (size_t)n_blocks * line_size;
-  SC2_CUDA(cudaMalloc(&d_lines, bytes ? bytes : 16));
-  if (h_sizes) SC2_CUDA(cudaMalloc(&d_sizes, (n_blocks ? n_blocks : 1) * sizeof(uint16_t)));
-  if (bytes) SC2_CUDA(cudaMemcpy(d_lines, h_lines, bytes, cudaMemcpyHostToDevice));
-  int rc = mpc_sc2_run_device(device, d_lines, n_blocks, line_size, sampling_lines, d_sizes, out, kernel_ms);
-  if (rc == MPC_OK && h_sizes && n_blocks) cudaMemcpy(h_sizes, d_sizes, n_blocks * sizeof(uint16_t), cudaMemcpyDeviceToHost);
-  cudaFree(d_lines);
-  if (d_sizes) cudaFree(d_sizes);
-  return rc;
+  SC2_CUDA(cudaMalloc(&d_lines, (size_t)cap * line_size));
+  if (h_sizes && cudaMalloc(&d_sizes, (size_t)cap * sizeof(uint16_t)) != cudaSuccess) { cudaFree(d_lines); return fail(MPC_E_CUDA, "cudaMalloc (sizes)"); }
+  auto done = [&](int rc) { cudaFree(d_lines); if (d_sizes) cudaFree(d_sizes); return rc; };
+  mpc_sc2_table table;
+  memset(&table, 0, sizeof(table));
+  float ms_total = 0;
+  if (build) {
+    if (cudaMemcpy(d_lines, h_lines, (size_t)sampling_lines * line_size, cudaMemcpyHostToDevice) != cudaSuccess) return done(fail(MPC_E_CUDA, "H2D copy of the sampling window"));
+    const int rc = mpc_sc2_build_table(device, d_lines, sampling_lines, line_size, &table);
+    if (rc != MPC_OK) return done(rc);
+  }
+  memset(out, 0, sizeof(*out));
+  for (uint64_t lo = 0; lo < n_blocks || lo == 0; lo += chunk) {
+    const uint64_t nb = std::min<uint64_t>(chunk, n_blocks - lo);
+    if (nb && cudaMemcpy(d_lines, h_lines + lo * line_size, (size_t)nb * line_size, cudaMemcpyHostToDevice) != cudaSuccess) return done(fail(MPC_E_CUDA, "H2D copy"));
+    mpc_variant_stats part;
+    float ms = 0;
+    const int rc = mpc_sc2_apply_device(device, d_lines, nb, lo, sampling_lines, line_size, &table, d_sizes, &part, &ms);
+    if (rc != MPC_OK) return done(rc);
+    if (h_sizes && nb && cudaMemcpy(h_sizes + lo, d_sizes, (size_t)nb * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) return done(fail(MPC_E_CUDA, "D2H copy"));
+    out->blocks += part.blocks;
+    out->original_bits += part.original_bits;
+    out->compressed_bits += part.compressed_bits;
+    out->counts[0] = part.counts[0];
+    ms_total += ms;
+    if (n_blocks == 0) break;
+  }
+  if (kernel_ms) *kernel_ms = ms_total;
+  return done(MPC_OK);
 }
 
 // CPACK: host, sequential (see the file header).  counts = ZZZZ, XXXX, MMMM, MMXX, ZZZX, MMMX (CPACK.h:119-127).

@@ -624,6 +624,38 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   t.tma = t.stages == 1 && (e = getenv("MPC_SPEC_TMA")) && e[0] == '1';
   t.smem_bytes = (size_t)t.warps * t.stages * 4096 + (t.tma ? (size_t)((t.warps * 8 + 15) / 16) * 16 : 0) + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
                  (t.use_lut ? 65536 : 0);
+  // Regrouping queues (mpc_spec.cuh): one queue per PredComp module in the shared memory that is left (227 KiB per CTA on sm_100,
+  // 1 KiB of it reserved by the driver); an entry is the block (128 B) + its index + a flag word.  At least two batches of 32 per
+  // queue, else the kernel runs without them (MPC_SPEC_REGROUP=0 switches them off for A/B runs).
+  {
+    const int nq = (int)mods.size();
+    const size_t limit = 227 * 1024 - 1024;
+    int cap = 0;
+    if (nq >= 2 && t.smem_bytes + 64 < limit) {
+      cap = (int)((limit - t.smem_bytes - (size_t)nq * 16 - 16 - 128) / ((size_t)nq * 136));
+      cap = cap / 32 * 32;
+      if (cap > 128) cap = 128;
+      if (cap < 64) cap = 0;
+    }
+    // Measured on B200 (profiles/r02_regroup.txt): the queues cost more than they save -- the part of the winner pass that
+    // divergent lanes do not already share (the per-module residue pass) is ~260 warp instructions per mixed tile, the queue
+    // traffic ~300, and warps that run different modules' passes at the same time overflow the 32 KiB instruction cache
+    // (F4 mixed 2 524 -> 1 697 GB/s, homogeneous classes -10 %).  They are therefore OFF unless MPC_SPEC_REGROUP=1 asks.
+    if (!((e = getenv("MPC_SPEC_REGROUP")) && e[0] == '1')) cap = 0;
+    if ((e = getenv("MPC_SPEC_QUEUE_CAP")) && atoi(e) > 0 && atoi(e) % 32 == 0 && atoi(e) <= cap) cap = atoi(e);
+    t.queue_cap = cap;
+    if (cap > 0) t.smem_bytes += (size_t)nq * cap * 136 + (size_t)nq * 16 + 16 + 128;
+    // With regrouping a warp's lanes mostly run ONE module's winner pass, so the row classifier no longer has to be shared
+    // across modules behind a reconvergence point: each module's pass runs straight into its own copy of the classifier and the
+    // 32 row words never have to be live all at once next to the block (no spills at 96 registers; MPC_SPEC_FUSED=0/1 overrides).
+    t.fused_encode = cap > 0 && !has_pm;
+    if ((e = getenv("MPC_SPEC_FUSED"))) t.fused_encode = e[0] == '1';
+    // Column-major configs get BOTH forms: a warp whose stage-3 lanes all picked the same module (homogeneous data -- the
+    // common case) runs that module's fused pass, any other warp the per-module residue passes followed by the ONE shared
+    // classifier (measured: fused +1.5 % on smooth / random data, shared +25 % on finely mixed data; MPC_SPEC_ADAPTIVE=0/1).
+    t.adaptive_encode = !t.fused_encode && !has_pm && t.use_lut;
+    if ((e = getenv("MPC_SPEC_ADAPTIVE"))) t.adaptive_encode = e[0] == '1' && !t.fused_encode;
+  }
   return t;
 }
 
@@ -682,6 +714,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   out.push_back(fmt("  static constexpr int kLutXor = %d;  // 0: table indexed by scan rows; 1 / 2: XOR stage (consecutive / first-plane) folded into the table",
                     t.use_lut ? t.lut_xor : 0));
   out.push_back(fmt("  static constexpr int kMinCtasPerSm = %d;  // __launch_bounds__: register budget 65536 / (threads * CTAs)", t.min_ctas));
+  out.push_back(fmt("  static constexpr int kQueueCap = %d;  // entries per regrouping queue (one queue per PredComp module); 0 = no regrouping", t.queue_cap));
   out.push_back("  __device__ static __forceinline__ uint32_t enc(int k) {  // encoding bits of cluster k-1, VPC.cpp:102-117");
   out.push_back("    switch (k) {");
   for (int k = 0; k <= n; k++) out.push_back(fmt("      case %d: return %du;", k, cfg.enc_bits[k]));
@@ -703,7 +736,8 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   }
   out.push_back("  }");
   out.push_back("  // residue sums (VPC.cpp:417-443) + common encoder (FPCModule.cpp:19-85) of the chosen module");
-  out.push_back("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq, unsigned lanes, const uint8_t* lut) {");
+  out.push_back(fmt("  static constexpr bool kAdaptiveEncode = %s;  // homogeneous warps run a fused per-module pass, others the shared classifier", t.adaptive_encode ? "true" : "false"));
+  out.push_back("  __device__ static __forceinline__ uint32_t encode(int best, const uint32_t (&x)[32], uint32_t& sa, uint32_t& sq, unsigned lanes, const uint8_t* lut, bool uniform) {");
   out.push_back("    uint32_t c[32];");
   // encoder families in use: column-major, or plane-major with a given pair of plane selectors
   std::vector<std::pair<int, std::pair<unsigned, unsigned>>> fams;
@@ -713,19 +747,37 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   for (auto& m : mods)
     if (std::find(fams.begin(), fams.end(), fam_of(m)) == fams.end()) fams.push_back(fam_of(m));
   std::sort(fams.begin(), fams.end());
-  out.push_back("    int fam = 0;");
-  out.push_back("    switch (best) {");
-  for (auto& m : mods) {
-    const int fid = (int)(std::find(fams.begin(), fams.end(), fam_of(m)) - fams.begin());
-    out.push_back(fmt("      case %d: full_%d(x, c, sa, sq); fam = %d; break;", m.idx, m.idx, fid));
-  }
-  out.push_back("      default: break;");
-  out.push_back("    }");
-  out.push_back("    __syncwarp(lanes);  // the row classifier below is shared by all modules: run it once per warp");
   auto call = [&](const std::pair<int, std::pair<unsigned, unsigned>>& f) {
     return f.first == 0 ? std::string(lay.paired ? "encode_rows(c, lut)" : "encode_cm<kUseLut, kSkipZeroGroups>(c, lut)")
                         : fmt("encode_pm<0x%04xu, 0x%04xu>(c)", f.second.first, f.second.second);
   };
+  if (t.adaptive_encode) {
+    out.push_back("    if (uniform) {  // every lane of the warp runs the same module: straight from its residue pass into the classifier");
+    out.push_back("      switch (best) {");
+    for (auto& m : mods) {
+      const int fid = (int)(std::find(fams.begin(), fams.end(), fam_of(m)) - fams.begin());
+      out.push_back(fmt("        case %d: full_%d(x, c, sa, sq); return %s;", m.idx, m.idx, call(fams[(size_t)fid]).c_str()));
+    }
+    out.push_back("        default: return 0u;");
+    out.push_back("      }");
+    out.push_back("    }");
+  } else {
+    out.push_back("    (void)uniform;");
+  }
+  out.push_back("    int fam = 0;");
+  out.push_back("    switch (best) {");
+  for (auto& m : mods) {
+    const int fid = (int)(std::find(fams.begin(), fams.end(), fam_of(m)) - fams.begin());
+    if (t.fused_encode) out.push_back(fmt("      case %d: full_%d(x, c, sa, sq); return %s;", m.idx, m.idx, call(fams[(size_t)fid]).c_str()));
+    else out.push_back(fmt("      case %d: full_%d(x, c, sa, sq); fam = %d; break;", m.idx, m.idx, fid));
+  }
+  out.push_back("      default: break;");
+  out.push_back("    }");
+  if (t.fused_encode) {
+    out.push_back("    (void)fam; (void)lanes; (void)lut;");
+    out.push_back("    return 0u;");
+  } else {
+  out.push_back("    __syncwarp(lanes);  // the row classifier below is shared by all modules: run it once per warp");
   if (fams.size() == 1) {
     out.push_back("    (void)fam;");
     out.push_back("    return " + call(fams[0]) + ";");
@@ -733,6 +785,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     for (size_t i = 0; i < fams.size(); i++) out.push_back(fmt("    if (fam == %d) return %s;", (int)i, call(fams[i]).c_str()));
     if (fams.empty()) out.push_back("    (void)fam; (void)c; (void)x; (void)sa; (void)sq; (void)lut;");
     out.push_back("    return 0u;");
+  }
   }
   out.push_back("  }");
   out.push_back("};");

@@ -16,6 +16,9 @@ struct SpecTraits {
   int min_ctas = 2;              // __launch_bounds__ second argument
   bool skip_zero_groups = true;  // encoder branches around groups of eight zero rows
   bool tma = false;              // tiles arrive by one TMA tensor copy per warp (cp.async.bulk.tensor + mbarrier) instead of 8 cp.async per lane
+  int queue_cap = 0;             // entries per regrouping queue (mpc_spec.cuh), 0 = none
+  bool fused_encode = false;     // every module's winner pass runs into its own copy of the row classifier
+  bool adaptive_encode = false;  // fused passes for warps whose lanes agree on the module, the shared classifier otherwise
   size_t smem_bytes = 0;         // dynamic shared memory of one CTA
 };
 

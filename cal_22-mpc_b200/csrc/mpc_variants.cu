@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "mpc_capi.h"
@@ -101,6 +102,19 @@ cudaError_t launch_variant(const uint8_t* d_lines, uint64_t n, uint16_t* d_sizes
 
 extern "C" const char* mpc_variant_error(void) { return mpc::g_verr.c_str(); }
 
+namespace mpc {
+namespace {
+// per-device counters + timing events, created once per process (no allocation or event creation per call)
+struct VariantWorkspace {
+  bool ready = false;
+  unsigned long long* d_stats = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+std::mutex g_vws_mutex;
+VariantWorkspace g_vws[16];
+}  // namespace
+}  // namespace mpc
+
 extern "C" int mpc_variant_run_device(int alg, int device, const uint8_t* d_lines, uint64_t n_blocks, uint32_t line_size,
                                       uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms) {
   using namespace mpc;
@@ -108,31 +122,32 @@ extern "C" int mpc_variant_run_device(int alg, int device, const uint8_t* d_line
   if (alg < MPC_ALG_BDI || alg > MPC_ALG_BPC) { g_verr = "unknown algorithm id"; return MPC_E_ARG; }
   if (line_size != 128) { g_verr = "the GPU variants are built for 128-byte blocks"; return MPC_E_ARG; }
   if ((uintptr_t)d_lines & 15) { g_verr = "lines must be 16-byte aligned"; return MPC_E_ARG; }
+  if (device < 0 || device >= 16) { g_verr = "device index out of range"; return MPC_E_ARG; }
+  std::lock_guard<std::mutex> lock(g_vws_mutex);
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return vfail(MPC_E_CUDA, "cudaSetDevice", e);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  unsigned long long* d_stats = nullptr;
-  if ((e = cudaMalloc(&d_stats, (1 + kCounters) * sizeof(unsigned long long))) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMalloc", e);
-  cudaMemset(d_stats, 0, (1 + kCounters) * sizeof(unsigned long long));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventRecord(e0, 0);
-  if (n_blocks) {
-    if (alg == MPC_ALG_BDI) e = launch_variant<MPC_ALG_BDI>(d_lines, n_blocks, d_sizes, d_stats, sms, 0);
-    else if (alg == MPC_ALG_FPC) e = launch_variant<MPC_ALG_FPC>(d_lines, n_blocks, d_sizes, d_stats, sms, 0);
-    else e = launch_variant<MPC_ALG_BPC>(d_lines, n_blocks, d_sizes, d_stats, sms, 0);
+  VariantWorkspace& w = g_vws[device];
+  if (!w.ready) {
+    if ((e = cudaMalloc(&w.d_stats, (1 + kCounters) * sizeof(unsigned long long))) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMalloc", e);
+    if ((e = cudaEventCreate(&w.e0)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaEventCreate", e);
+    if ((e = cudaEventCreate(&w.e1)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaEventCreate", e);
+    w.ready = true;
   }
-  cudaEventRecord(e1, 0);
+  if ((e = cudaMemsetAsync(w.d_stats, 0, (1 + kCounters) * sizeof(unsigned long long), 0)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMemsetAsync", e);
+  if ((e = cudaEventRecord(w.e0, 0)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaEventRecord", e);
+  if (n_blocks) {
+    if (alg == MPC_ALG_BDI) e = launch_variant<MPC_ALG_BDI>(d_lines, n_blocks, d_sizes, w.d_stats, sms, 0);
+    else if (alg == MPC_ALG_FPC) e = launch_variant<MPC_ALG_FPC>(d_lines, n_blocks, d_sizes, w.d_stats, sms, 0);
+    else e = launch_variant<MPC_ALG_BPC>(d_lines, n_blocks, d_sizes, w.d_stats, sms, 0);
+    if (e != cudaSuccess) return vfail(MPC_E_CUDA, "variant kernel launch", e);
+  }
+  if ((e = cudaEventRecord(w.e1, 0)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaEventRecord", e);
   unsigned long long h[1 + kCounters];
-  if (e == cudaSuccess) e = cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+  if ((e = cudaMemcpy(h, w.d_stats, sizeof(h), cudaMemcpyDeviceToHost)) != cudaSuccess) return vfail(MPC_E_CUDA, "variant kernel", e);
   float ms = 0.f;
-  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d_stats);
-  if (e != cudaSuccess) return vfail(MPC_E_CUDA, "variant kernel", e);
+  if ((e = cudaEventElapsedTime(&ms, w.e0, w.e1)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaEventElapsedTime", e);
   memset(out, 0, sizeof(*out));
   out->blocks = n_blocks;
   out->original_bits = n_blocks * 8ull * line_size;  // CompResult::OriginalSize
@@ -142,24 +157,40 @@ extern "C" int mpc_variant_run_device(int alg, int device, const uint8_t* d_line
   return MPC_OK;
 }
 
+// Host dump: streamed through one device buffer in 256 MiB chunks (dumps larger than HBM work), every copy checked.
 extern "C" int mpc_variant_run_host(int alg, int device, const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size,
                                     uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms) {
   using namespace mpc;
-  if (n_blocks && !h_lines) { g_verr = "null lines"; return MPC_E_ARG; }
+  if (!out || (n_blocks && !h_lines)) { g_verr = "null argument"; return MPC_E_ARG; }
+  if (line_size != 128) { g_verr = "the GPU variants are built for 128-byte blocks"; return MPC_E_ARG; }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return vfail(MPC_E_CUDA, "cudaSetDevice", e);
+  const uint64_t chunk = (256ull << 20) / line_size;
+  const uint64_t cap = n_blocks < chunk ? (n_blocks ? n_blocks : 1) : chunk;
   uint8_t* d_lines = nullptr;
   uint16_t* d_sizes = nullptr;
-  const size_t bytes = (size_t)n_blocks * line_size;
-  if ((e = cudaMalloc(&d_lines, bytes ? bytes : 16)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMalloc", e);
-  if (h_sizes && (e = cudaMalloc(&d_sizes, (n_blocks ? n_blocks : 1) * sizeof(uint16_t))) != cudaSuccess) {
+  if ((e = cudaMalloc(&d_lines, (size_t)cap * line_size)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMalloc", e);
+  if (h_sizes && (e = cudaMalloc(&d_sizes, (size_t)cap * sizeof(uint16_t))) != cudaSuccess) {
     cudaFree(d_lines);
     return vfail(MPC_E_CUDA, "cudaMalloc", e);
   }
-  if (bytes) cudaMemcpy(d_lines, h_lines, bytes, cudaMemcpyHostToDevice);
-  int rc = mpc_variant_run_device(alg, device, d_lines, n_blocks, line_size, d_sizes, out, kernel_ms);
-  if (rc == MPC_OK && h_sizes && n_blocks) cudaMemcpy(h_sizes, d_sizes, n_blocks * sizeof(uint16_t), cudaMemcpyDeviceToHost);
-  cudaFree(d_lines);
-  if (d_sizes) cudaFree(d_sizes);
-  return rc;
+  auto done = [&](int rc) { cudaFree(d_lines); if (d_sizes) cudaFree(d_sizes); return rc; };
+  memset(out, 0, sizeof(*out));
+  float ms_total = 0.f;
+  for (uint64_t lo = 0; lo < n_blocks; lo += chunk) {
+    const uint64_t nb = n_blocks - lo < chunk ? n_blocks - lo : chunk;
+    if ((e = cudaMemcpy(d_lines, h_lines + lo * line_size, (size_t)nb * line_size, cudaMemcpyHostToDevice)) != cudaSuccess) return done(vfail(MPC_E_CUDA, "H2D copy", e));
+    mpc_variant_stats part;
+    float ms = 0.f;
+    const int rc = mpc_variant_run_device(alg, device, d_lines, nb, line_size, d_sizes, &part, &ms);
+    if (rc != MPC_OK) return done(rc);
+    if (h_sizes && (e = cudaMemcpy(h_sizes + lo, d_sizes, (size_t)nb * sizeof(uint16_t), cudaMemcpyDeviceToHost)) != cudaSuccess) return done(vfail(MPC_E_CUDA, "D2H copy", e));
+    out->blocks += part.blocks;
+    out->original_bits += part.original_bits;
+    out->compressed_bits += part.compressed_bits;
+    for (int i = 0; i < 16; i++) out->counts[i] += part.counts[i];
+    ms_total += ms;
+  }
+  if (kernel_ms) *kernel_ms = ms_total;
+  return done(MPC_OK);
 }

@@ -86,11 +86,18 @@ MPC_HD uint32_t bdi_check(const uint32_t (&x)[32], uint32_t* imm_out = nullptr) 
       base = im ? base : v;
     }
     imm = (uint32_t)popc32(imm_mask);
+    // deltas against the base, four values at a time: the first value out of range decides the check, so the rest is
+    // skipped (incompressible data -- most of a dump -- leaves after the first group)
 #pragma unroll
-    for (int i = 0; i < n; i++) {
-      const uint64_t v = bdi_value<8>(x, i);
-      // immediates are skipped; the base itself passes (difference 0)
-      not_all |= !((imm_mask >> i) & 1u) && !bdi_fits64<D>(base - v);
+    for (int g = 0; g < n; g += 4) {
+      if (!not_all) {
+#pragma unroll
+        for (int i = g; i < g + 4; i++) {
+          const uint64_t v = bdi_value<8>(x, i);
+          // immediates are skipped; the base itself passes (difference 0)
+          not_all |= !((imm_mask >> i) & 1u) && !bdi_fits64<D>(base - v);
+        }
+      }
     }
   } else {
     constexpr uint32_t limit = D == 1 ? 0xffu : 0xffffu;  // zero-extended values are never negative
@@ -103,9 +110,14 @@ MPC_HD uint32_t bdi_check(const uint32_t (&x)[32], uint32_t* imm_out = nullptr) 
       base = im ? base : v;
     }
 #pragma unroll
-    for (int i = 0; i < n; i++) {
-      const uint32_t v = (uint32_t)bdi_value<B>(x, i);
-      not_all |= v > limit && !bdi_delta_fits32<D>(base, v);
+    for (int g = 0; g < n; g += 8) {
+      if (!not_all) {
+#pragma unroll
+        for (int i = g; i < g + 8; i++) {
+          const uint32_t v = (uint32_t)bdi_value<B>(x, i);
+          not_all |= v > limit && !bdi_delta_fits32<D>(base, v);
+        }
+      }
     }
   }
   if (imm_out) *imm_out = imm;

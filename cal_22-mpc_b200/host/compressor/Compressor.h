@@ -28,6 +28,12 @@ class Compressor {
       CompressLine(line);
     }
   }
+  // file-backed form: nLines consecutive lines starting at byte `offset` of the open descriptor fd.  false = not supported by
+  // this compressor (the driver then hands the lines over with CompressBatch).
+  virtual bool CompressFile(int fd, uint64_t offset, uint64_t nLines, bool directIo) {
+    (void)fd; (void)offset; (void)nLines; (void)directIo;
+    return false;
+  }
   virtual CompResult* GetResult() { return m_Stat; }
 
  protected:

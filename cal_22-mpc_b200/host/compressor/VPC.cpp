@@ -99,6 +99,7 @@ VPC::VPC(std::string configPath, int numGpus, int kernel) {
     mpc_ctx* c = nullptr;
     if (mpc_create(&m_Cfg, d, &c) != MPC_OK) die("mpc_create", nullptr);
     if (kernel && mpc_set_kernel(c, kernel) != MPC_OK) die("mpc_set_kernel", c);
+    if (mpc_prepare_host(c) != MPC_OK) die("mpc_prepare_host", c);  // pin the staging ring while the loader parses its header
     m_Ctx.push_back(c);
   }
   // communicators are created once per compressor, not per GetResult()
@@ -140,12 +141,38 @@ void VPC::CompressBatch(const uint8_t* lines, uint64_t nLines) {
     if (G == 1) work(); else th.emplace_back(work);
   }
   for (auto& t : th) t.join();
+  collectTiming();
+}
+
+void VPC::collectTiming() {
+  const size_t G = m_Ctx.size();
   for (mpc_ctx* c : m_Ctx) {
     float ms = 0;
     int launches = 0;
     mpc_last_timing(c, &ms, &launches);
     if (ms > m_KernelMs || G == 1) m_KernelMs = (G == 1) ? m_KernelMs + ms : ms;
   }
+}
+
+// The file-backed hand-over: every GPU reads its contiguous shard of the byte range itself (mpc_submit_file), so the dump is
+// neither mapped nor copied through an intermediate buffer on its way to the pinned staging ring.
+bool VPC::CompressFile(int fd, uint64_t offset, uint64_t nLines, bool directIo) {
+  const size_t G = m_Ctx.size();
+  const uint64_t per = (nLines + G - 1) / G;
+  std::vector<std::thread> th;
+  for (size_t g = 0; g < G; g++) {
+    const uint64_t lo = std::min<uint64_t>(nLines, g * per), hi = std::min<uint64_t>(nLines, (g + 1) * per);
+    if (hi == lo) continue;
+    auto work = [this, g, lo, hi, fd, offset, directIo]() {
+      if (mpc_submit_file(m_Ctx[g], fd, offset + lo * (uint64_t)m_Cfg.line_size, hi - lo, nullptr, directIo ? 1 : 0) != MPC_OK ||
+          mpc_sync(m_Ctx[g]) != MPC_OK)
+        die("CompressFile", m_Ctx[g]);
+    };
+    if (G == 1) work(); else th.emplace_back(work);
+  }
+  for (auto& t : th) t.join();
+  collectTiming();
+  return true;
 }
 
 CompResult* VPC::GetResult() {

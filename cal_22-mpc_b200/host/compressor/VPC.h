@@ -53,12 +53,14 @@ class VPC : public Compressor {
   int GetNumClusters() { return m_Cfg.num_modules + 1; }
   unsigned CompressLine(std::vector<uint8_t>& dataLine) override;       // VPC.cpp:22-25
   void CompressBatch(const uint8_t* lines, uint64_t nLines) override;  // replaces main.cpp:237-243
+  bool CompressFile(int fd, uint64_t offset, uint64_t nLines, bool directIo) override;  // pread -> pinned ring -> H2D -> kernel
   CompResult* GetResult() override;
   double KernelMs() const { return m_KernelMs; }
   const char* KernelName() const;
 
  private:
   void die(const char* what, mpc_ctx* ctx);
+  void collectTiming();
   mpc_config_pod m_Cfg;
   std::vector<mpc_ctx*> m_Ctx;
   double m_KernelMs = 0;

@@ -66,6 +66,10 @@ class Loader {
   // zero-copy form for loaders that hold the lines contiguously: pointer to the remaining lines, count
   // in *nLines, and the cursor moves to the end.  nullptr if unsupported.
   virtual const uint8_t* GetAll(uint64_t* nLines) { *nLines = 0; return nullptr; }
+  // file-backed form for loaders whose remaining lines are one contiguous byte range of a file: an open descriptor (owned
+  // by the loader), the range's offset and the line count; the cursor moves to the end.  -1 if unsupported.  The compressor
+  // reads the range itself, straight into its pinned staging buffers (comp::Compressor::CompressFile).
+  virtual int GetFile(uint64_t* dataOffset, uint64_t* nLines, bool directIo = false) { (void)directIo; *dataOffset = 0; *nLines = 0; return -1; }
 
  protected:
   const std::string m_FilePath;

@@ -1,3 +1,6 @@
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE  // O_DIRECT
+#endif
 #include "LoaderNPY.h"
 
 #include <fcntl.h>
@@ -13,6 +16,8 @@ LoaderNPY::LoaderNPY(const std::string& filePath) : Loader(filePath) { Reset(); 
 LoaderNPY::~LoaderNPY() { unmap(); }
 
 void LoaderNPY::unmap() {
+  if (m_Fd >= 0) close(m_Fd);
+  m_Fd = -1;
   if (m_Map) munmap(const_cast<uint8_t*>(m_Map), m_MapBytes);
   m_Map = nullptr;
   m_Data = nullptr;
@@ -98,6 +103,22 @@ const uint8_t* LoaderNPY::GetAll(uint64_t* nLines) {
   *nLines = usable - m_CurrentLine;
   m_CurrentLine = usable;
   return p;
+}
+
+int LoaderNPY::GetFile(uint64_t* dataOffset, uint64_t* nLines, bool directIo) {
+  *dataOffset = 0;
+  *nLines = 0;
+  if (!m_Data) return -1;
+  if (m_Fd >= 0) close(m_Fd);
+  m_Fd = open(m_FilePath.c_str(), O_RDONLY | (directIo ? O_DIRECT : 0));
+  if (m_Fd < 0) return -1;
+  const uint64_t usable = m_Rows ? m_Rows - 1 : 0;  // the last row is never compressed (see GetCacheline)
+  if (m_CurrentLine < usable) {
+    *dataOffset = (uint64_t)(m_Data - m_Map) + m_CurrentLine * m_LineSize;
+    *nLines = usable - m_CurrentLine;
+    m_CurrentLine = usable;
+  }
+  return m_Fd;
 }
 
 }  // namespace trace

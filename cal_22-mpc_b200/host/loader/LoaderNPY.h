@@ -18,6 +18,7 @@ class LoaderNPY : public Loader {
   void Reset() override;                              // LoaderNPY.cpp:48-54
   uint64_t GetChunk(uint8_t* dst, uint64_t maxLines) override;
   const uint8_t* GetAll(uint64_t* nLines) override;
+  int GetFile(uint64_t* dataOffset, uint64_t* nLines, bool directIo = false) override;
   const std::string& Error() const { return m_Error; }
 
  private:
@@ -25,6 +26,7 @@ class LoaderNPY : public Loader {
   const uint8_t* m_Map = nullptr;
   size_t m_MapBytes = 0;
   const uint8_t* m_Data = nullptr;
+  int m_Fd = -1;  // descriptor handed to CompressFile (opened on demand)
   uint64_t m_Rows = 0, m_LineSize = 0, m_CurrentLine = 0;
   std::string m_Error;
 };

@@ -5,6 +5,7 @@
 //   compressor -a VPC -i FILE.npy -c CFG.json [-o OUTDIR] [--gpus N] [--kernel 0|1|2] [--time]
 #include <cassert>
 #include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -129,6 +130,19 @@ int main(int argc, char** argv) {
 // main.cpp:208-248 with the GetCacheline/CompressLine pair replaced by GetChunk/CompressBatch
 comp::CompResult* compressLines(comp::Compressor* compressor, trace::Loader* loader, unsigned lineSize) {
   uint64_t n = 0;
+  // 1. file-backed loaders and compressors that read files themselves: descriptor + byte range, no mapping, no copy
+  {
+    const char* mode = getenv("MPC_IO");  // "mmap": skip this path; "direct": O_DIRECT reads (cold dumps, no page cache)
+    const bool direct = mode && std::string(mode) == "direct";
+    if (!(mode && std::string(mode) == "mmap")) {
+      uint64_t off = 0;
+      const int fd = loader->GetFile(&off, &n, direct);
+      if (fd >= 0) {
+        if (n == 0 || compressor->CompressFile(fd, off, n, direct)) return compressor->GetResult();
+        loader->Reset();  // the compressor does not read files: start over with the in-memory forms
+      }
+    }
+  }
   const uint8_t* all = loader->GetAll(&n);
   if (all) {
     if (n) compressor->CompressBatch(all, n);  // the mapped file is handed over whole; the library chunks it

@@ -118,11 +118,24 @@ int mpc_set_stream(mpc_ctx* ctx, void* cuda_stream);
  * Asynchronous on the context's stream; statistics accumulate on the device. */
 int mpc_submit_device(mpc_ctx* ctx, const uint8_t* d_lines, uint64_t n_blocks, uint16_t* d_packed);
 
-/* Blocks in host memory (pageable or pinned).  Chunked, double-buffered: pinned staging ->
- * cudaMemcpyAsync H2D on alternating streams overlapped with the kernel.  h_packed (optional,
+/* Blocks in host memory (pageable or pinned).  Chunked through a ring of three pinned
+ * staging slots: cudaMemcpyAsync H2D on rotating streams overlapped with the kernel.  h_packed (optional,
  * host) receives the per-block results.  Returns after the last chunk has been issued;
  * mpc_finish() / mpc_sync() wait for completion. */
 int mpc_submit_host(mpc_ctx* ctx, const uint8_t* h_lines, uint64_t n_blocks, uint16_t* h_packed);
+
+/* Blocks in a FILE: n_blocks * line_size bytes starting at file_offset of the open descriptor fd (the data part of an .npy
+ * dump, a raw dump ...).  Replaces LoaderNPY's "read the whole file into a vector, then copy one line per call"
+ * (LoaderNPY.cpp:14-34, 48-54) for dumps of any size, including dumps larger than host memory: the file is read with
+ * pread() on several threads STRAIGHT into the context's pinned staging ring (three 32 MiB slots: while one slot is
+ * being filled, the previous one is on its way over PCIe and the one before is being compressed), so the data is touched
+ * once on the host and never mapped.  direct_io != 0: fd was opened with O_DIRECT (cold dumps that should not go through
+ * the page cache); offsets and lengths are aligned internally.  Returns after the last chunk has been issued. */
+int mpc_submit_file(mpc_ctx* ctx, int fd, uint64_t file_offset, uint64_t n_blocks, uint16_t* h_packed, int direct_io);
+
+/* Allocate the staging ring of mpc_submit_host / mpc_submit_file now (pinning host memory takes tens of milliseconds) instead
+ * of inside the first submit. */
+int mpc_prepare_host(mpc_ctx* ctx);
 
 /* Wait for all submitted work. */
 int mpc_sync(mpc_ctx* ctx);
@@ -214,6 +227,18 @@ int mpc_sc2_run_device(int device, const uint8_t* d_lines, uint64_t n_blocks, ui
 int mpc_sc2_run_host(int device, const uint8_t* h_lines, uint64_t n_blocks, uint32_t line_size, uint64_t sampling_lines,
                      uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms);
 const char* mpc_sc2_error(void);
+/* The two phases on their own, for sharded runs: the GPU that holds the first sampling_lines lines
+ * builds the code table, the table (at most 1024 x (symbol, length), plain host data) is handed to every shard -- by whatever
+ * the job uses to broadcast -- and each shard applies it to its lines; first_block = index of the shard's first line in the
+ * dump, so that the sampling lines (33 bits per word) are counted where they are. */
+typedef struct {
+  uint32_t n;              /* symbols that received a code (<= 1024) */
+  uint32_t symbols[1024];  /* ascending */
+  uint8_t lengths[1024];   /* Huffman code length = leaf depth, SC2.cpp:150-162 */
+} mpc_sc2_table;
+int mpc_sc2_build_table(int device, const uint8_t* d_lines, uint64_t sampling_lines, uint32_t line_size, mpc_sc2_table* table);
+int mpc_sc2_apply_device(int device, const uint8_t* d_lines, uint64_t n_blocks, uint64_t first_block, uint64_t sampling_lines,
+                         uint32_t line_size, const mpc_sc2_table* table, uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms);
 
 /* CPACK (CPACK.cpp:7-101): the 16-entry dictionary persists across lines, so the result depends on every earlier word
  * -- sequential by construction; this entry point runs on the host and is reported as such.

@@ -152,7 +152,7 @@ def test_device_submit_and_synth_match_numpy(mpcb):
 
 
 def test_chunked_host_path_multiple_chunks(mpcb):
-    # > 2 chunks of 64 MiB so that both staging buffers are reused (LoaderNPY replacement path)
+    # more chunks (32 MiB each) than staging slots, so that every slot is reused (LoaderNPY replacement path)
     m = mpcb.Mpc(cfg_path("F4"))
     n = (160 << 20) // 128
     blocks = synth("mixed_regions", 5, 0, n, n)
@@ -343,3 +343,39 @@ def test_two_gpu_shards_allreduce_equals_oracle(mpcb):
     assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
     assert st.blocks == n and st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count)
     assert np.array_equal(st.res_abs, r.res_abs) and np.array_equal(st.hist[:, :r.hist.shape[1]], r.hist)
+
+
+@pytest.mark.parametrize("direct", [False, True])
+def test_submit_file_reads_the_dump_itself(mpcb, tmp_path, direct):
+    """mpc_submit_file: pread straight into the pinned staging ring (more chunks than staging slots, an
+    unaligned data offset like an .npy header's, O_DIRECT on and off) -- per-block results and statistics equal the oracle's."""
+    import os
+    n = (200 << 20) // 128 + 777
+    blocks = synth("mixed_regions", 9, 0, n, n)
+    path = str(tmp_path / "dump.bin")
+    header = b"\x93NUMPY-like header of an odd length....."  # 40 bytes: the data starts unaligned
+    with open(path, "wb") as f:
+        f.write(header)
+        f.write(blocks.tobytes())
+    flags = os.O_RDONLY | (os.O_DIRECT if direct else 0)
+    try:
+        fd = os.open(path, flags)
+    except OSError:
+        pytest.skip("O_DIRECT not supported by the file system under tmp_path")
+    try:
+        m = mpcb.Mpc(cfg_path("F4"))
+        packed = np.zeros(n, np.uint16)
+        m.reset()
+        try:
+            m.submit_file(fd, len(header), n, packed, direct_io=direct)
+        except mpcb.MpcError as e:
+            if direct and "short read" in str(e):
+                pytest.skip("O_DIRECT reads refused by the file system under tmp_path")
+            raise
+        st = m.finish()
+    finally:
+        os.close(fd)
+    r = OracleMPC(cfg_path("F4")).run(blocks)
+    sizes, sels = mpcb.unpack(packed)
+    assert np.array_equal(sizes, r.sizes) and np.array_equal(sels, r.sels)
+    assert st.blocks == n and st.CompressedSize == r.CompressedSize and np.array_equal(st.res_sq, r.res_sq)

@@ -141,3 +141,34 @@ def test_sc2_gpu_matches_oracle(mpcb, kind, n, S):
     assert bad.size == 0, (bad[:5], sizes[bad[:5]], want[bad[:5]])
     assert st.compressed_bits == int(want.astype(np.uint64).sum()) and st.original_bits == n * 1024
     assert mpcb.sc2_sampling_lines(n + 1) == max(10000, min((n + 1) // 100, 1000000))  # main.cpp:108-114
+
+
+@pytest.mark.gpu
+def test_sc2_two_phase_api_shards_like_one_pass(mpcb):
+    """SURVEY.md section 8e for SC2: the table comes from the shard that holds the sampling window, every shard applies it to
+    its own lines with its global offset -- per-line sizes and totals equal the one-pass result and the CPU oracle."""
+    import ctypes as C
+    import torch
+    from oracle.bridge import oracle_sc2
+    from tools.gen_dump import synth
+    n, S = 30000, 10000
+    blocks = synth("mixed_hashed", 99, 0, n, n)
+    want = oracle_sc2(blocks, S)
+    d = torch.from_numpy(blocks).cuda()
+    lib = mpcb.lib()
+    table = mpcb.capi.Sc2Table()
+    assert lib.mpc_sc2_build_table(0, d.data_ptr(), S, 128, C.byref(table)) == 0, lib.mpc_sc2_error()
+    assert 0 < table.n <= 1024
+    got = np.zeros(n, np.uint16)
+    total = 0
+    for lo, hi in ((0, 12345), (12345, n)):  # two "ranks"
+        sizes = torch.zeros(hi - lo, dtype=torch.int16, device="cuda")
+        st, ms = mpcb.VariantStats(), C.c_float()
+        rc = lib.mpc_sc2_apply_device(0, d.data_ptr() + lo * 128, hi - lo, lo, S, 128, C.byref(table), sizes.data_ptr(), C.byref(st), C.byref(ms))
+        assert rc == 0, lib.mpc_sc2_error()
+        got[lo:hi] = sizes.cpu().numpy().view(np.uint16)
+        total += st.compressed_bits
+    assert np.array_equal(got.astype(np.uint32), want)
+    assert total == int(want.astype(np.uint64).sum())
+    one, st1, _ = mpcb.sc2_run(blocks, S)
+    assert np.array_equal(one.astype(np.uint32), want) and st1.compressed_bits == total
