@@ -137,6 +137,11 @@ def _port_worker(args):
     from oracle.bridge import OracleMPC, oracle_variant
     from tools.gen_dump import synth
     blocks = synth(kind, seed, first, n, total)
+    if alg == "SC2":
+        from oracle.bridge import oracle_sc2
+        t0 = time.perf_counter()
+        sizes = oracle_sc2(blocks, 10000)
+        return time.perf_counter() - t0, n * BLOCK * 8, int(sizes.astype(np.uint64).sum())
     if alg != "VPC":
         t0 = time.perf_counter()
         sizes, _ = oracle_variant(alg, blocks)
@@ -548,19 +553,42 @@ def run_variants(job, d, n):
         tot = job.sum_over_ranks([vs.original_bits, vs.compressed_bits])
         res[alg] = {"value": job.world * n * BLOCK / (ms * 1e-3) / 1e9, "unit": "GB/s", "frac": (n * BLOCK / (ms * 1e-3) / 1e9) / job.peak,
                     "comp_ratio": tot[0] / tot[1] if tot[1] else None}
-    if job.world == 1:
-        S = mpcb.sc2_sampling_lines(n + 1)
-        vs, msf = mpcb.VariantStats(), C.c_float()
+    # SC2 is two-phase: the rank that holds the first S lines builds the code table (device sort +
+    # host tree), the table (<= 1024 symbols) is broadcast, every rank applies it to its shard
+    total_lines = n * job.world
+    S = mpcb.sc2_sampling_lines(total_lines + 1)
+    if S <= n:
+        lib = mpcb.lib()
+        table = mpcb.capi.Sc2Table()
+        ms_build = 0.0
         for _ in range(2):
-            rc = mpcb.lib().mpc_sc2_run_device(job.local, d.data_ptr(), n, BLOCK, S, None, C.byref(vs), C.byref(msf))
-            if rc != 0:
-                raise SystemExit("SC2: " + mpcb.lib().mpc_sc2_error().decode())
-        res["SC2"] = {"value": n * BLOCK / (msf.value * 1e-3) / 1e9, "unit": "GB/s", "frac": (n * BLOCK / (msf.value * 1e-3) / 1e9) / job.peak,
-                      "comp_ratio": vs.original_bits / vs.compressed_bits, "includes": f"device histogram of the first {S} lines, host tree, device lookup"}
+            job.barrier()
+            t0 = time.perf_counter()
+            if job.rank == 0:
+                if lib.mpc_sc2_build_table(job.local, d.data_ptr(), S, BLOCK, C.byref(table)) != 0:
+                    raise SystemExit("SC2: " + lib.mpc_sc2_error().decode())
+            if job.world > 1:
+                buf = [bytes(table) if job.rank == 0 else None]
+                job.dist.broadcast_object_list(buf, src=0)
+                C.memmove(C.byref(table), buf[0], C.sizeof(table))
+            ms_build = (time.perf_counter() - t0) * 1e3
+            vs, msf = mpcb.VariantStats(), C.c_float()
+            if lib.mpc_sc2_apply_device(job.local, d.data_ptr(), n, job.rank * n, S, BLOCK, C.byref(table), None, C.byref(vs), C.byref(msf)) != 0:
+                raise SystemExit("SC2: " + lib.mpc_sc2_error().decode())
+        ms_apply = job.max_over_ranks(msf.value)
+        ms_build = job.max_over_ranks(ms_build)
+        tot = job.sum_over_ranks([vs.original_bits, vs.compressed_bits])
+        ms = ms_build + ms_apply
+        res["SC2"] = {"value": job.world * n * BLOCK / (ms * 1e-3) / 1e9, "unit": "GB/s", "frac": (n * BLOCK / (ms * 1e-3) / 1e9) / job.peak,
+                      "comp_ratio": tot[0] / tot[1] if tot[1] else None, "table_ms": ms_build, "lookup_ms": ms_apply, "symbols": int(table.n),
+                      "includes": f"table from the first {S} lines on rank 0 (device sort + host tree, wall clock" +
+                                  (", broadcast" if job.world > 1 else "") + ") + device lookup over every shard"}
     if job.rank == 0 and job.a.cpu_baseline:
         cores = os.cpu_count() or 1
         with mp.get_context("spawn").Pool(cores) as pool:
-            for alg in ("BDI", "FPC", "BPC"):
+            for alg in ("BDI", "FPC", "BPC", "SC2"):
+                if alg not in res:
+                    continue
                 info = cpu_reference_pass(None, "mixed_hashed", 31337, n * job.world, job.a.ref_sample_blocks, pool, cores, alg=alg)
                 res[alg]["cpu_reference"] = {"value": info["bytes"] / info["wall_s"] / 1e9, "unit": "GB/s", "cores": cores, "kind": info["kind"],
                                              "sample_blocks": info["bytes"] // BLOCK, "ratio_on_sample": info["ratio"]}

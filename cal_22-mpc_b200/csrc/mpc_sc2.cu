@@ -52,9 +52,8 @@ sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t f
                   const uint8_t* __restrict__ g_lens, uint16_t* __restrict__ sizes, unsigned long long* __restrict__ total) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* s_stage = reinterpret_cast<uint4*>(smem_raw);
-  __shared__ uint32_t s_key[kHashSlots];
-  __shared__ uint8_t s_len[kHashSlots];
-  for (int i = threadIdx.x; i < kHashSlots; i += kThreads) { s_key[i] = g_keys[i]; s_len[i] = g_lens[i]; }
+  __shared__ uint2 s_tab[kHashSlots];  // (symbol, code length + 1), length field 0 = empty slot: one 8-byte load per probe
+  for (int i = threadIdx.x; i < kHashSlots; i += kThreads) s_tab[i] = make_uint2(g_keys[i], (uint32_t)g_lens[i]);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long bits = 0;
@@ -64,18 +63,30 @@ sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t f
     if (first_block + blk < sampling) {
       size = 33u * 32u;  // sampling phase: every word is a miss (SC2.cpp:315-323 with an empty code map)
     } else {
-#pragma unroll 8
+      // first probe of all 32 words with no branch in between (32 independent loads in flight); only a word whose first slot
+      // holds another symbol walks on
+      uint32_t pending = 0;  // bit j: word j has to look at further slots
+#pragma unroll
       for (int j = 0; j < 32; j++) {
-        const uint32_t v = x[j];
-        uint32_t idx = sc2_hash(v);
-        uint32_t len = 33u;
-        while (true) {
-          const uint32_t l = s_len[idx];
-          if (l == 0u) break;                                  // empty slot: not in the table
-          if (s_key[idx] == v) { len = l - 1u; break; }
-          idx = (idx + 1u) & (kHashSlots - 1);
+        const uint2 e = s_tab[sc2_hash(x[j])];
+        const bool hit = e.y != 0u && e.x == x[j];
+        size += hit ? e.y - 1u : 33u;
+        pending |= (e.y != 0u && !hit) ? (1u << j) : 0u;
+      }
+      if (pending) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          if ((pending >> j) & 1u) {
+            const uint32_t v = x[j];
+            uint32_t idx = (sc2_hash(v) + 1u) & (kHashSlots - 1);
+            while (true) {
+              const uint2 e = s_tab[idx];
+              if (e.y == 0u) break;                                    // empty slot: not in the table (33 already counted)
+              if (e.x == v) { size += e.y - 1u - 33u; break; }           // found after all: replace the 33
+              idx = (idx + 1u) & (kHashSlots - 1);
+            }
+          }
         }
-        size += len;
       }
     }
     if (valid) {

@@ -100,3 +100,39 @@ def test_tma_variant_compiles_with_nvrtc(mpcb, monkeypatch):
     monkeypatch.setenv("MPC_SPEC_TMA", "1")
     rc, nbytes, log = mpcb.jit_compile_check(cfg_path("F4"))
     assert rc == 0 and nbytes > 10000, log
+
+
+@pytest.mark.parametrize("flags", [{"MPC_SPEC_REGROUP": "1"}, {"MPC_SPEC_REGROUP": "1", "MPC_SPEC_FUSED": "0"}, {"MPC_SPEC_ADAPTIVE": "0"},
+                                   {"MPC_SPEC_FUSED": "1"}])
+def test_generation_variants_compile_with_nvrtc(mpcb, monkeypatch, flags):
+    """The generation-time switches of the specialised kernel (regrouping queues, fused / adaptive / shared winner pass)."""
+    for k, v in flags.items():
+        monkeypatch.setenv(k, v)
+    for cfg in ("F4", "P6"):
+        rc, nbytes, log = mpcb.jit_compile_check(cfg_path(cfg))
+        assert rc == 0 and nbytes > 10000, log
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 3, 5])
+def test_jit_kernels_with_regrouping_queues_match_oracle(mpcb, monkeypatch, seed):
+    """MPC_SPEC_REGROUP=1 (off by default: measured slower, profiles/r02_regroup.txt): warps whose lanes picked different
+    winners hand their blocks to per-module shared-memory queues; full batches of one module are taken by any warp, the
+    last warps drain the partial ones.  Finely mixed data keeps the queues busy; ragged counts exercise the drain."""
+    from tools.gen_dump import synth
+    monkeypatch.setenv("MPC_SPEC_REGROUP", "1")
+    monkeypatch.setenv("MPC_JIT_CACHE_DIR", "")
+    cfg = eligible_config(300 + seed)
+    while sum(1 for m in cfg["modules"].values() if m["name"] == "PredComp") < 2:  # queues need two modules to choose from
+        seed += 17
+        cfg = eligible_config(300 + seed)
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(cfg)))
+    assert m.kernel_name() == "spec_thread:jit"
+    rng = np.random.default_rng(seed)
+    for blocks in (random_blocks(rng, 33), random_blocks(rng, 40001), synth("mixed_hashed", 7, 0, 300007, 300007)):
+        sizes, sels, st = m.compress(blocks)
+        r = OracleMPC(cfg).run(blocks)
+        bad = np.nonzero((sizes != r.sizes) | (sels != r.sels))[0]
+        assert bad.size == 0, (len(blocks), bad[:5], sizes[bad[:5]], r.sizes[bad[:5]])
+        assert st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count)
+        assert np.array_equal(st.res_abs, r.res_abs) and np.array_equal(st.res_sq, r.res_sq)
