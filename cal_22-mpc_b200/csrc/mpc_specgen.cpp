@@ -250,7 +250,7 @@ struct Module {
 
   std::string g_from_r(int w, const std::string& r) const {
     if (cxor) return fmt("xc(%s, 0x%08xu)", r.c_str(), w == 0 ? 0x7f7f7f00u : 0x7f7f7f7fu);
-    return fmt("xf(%s, 0x%08xu)", r.c_str(), w == 0 ? 0x01010100u : 0x01010101u);
+    return fmt("xf(%s, 0x%08xu)", r.c_str(), w == 0 ? 0x7f7f7f00u : 0x7f7f7f7fu);
   }
 };
 
@@ -542,6 +542,161 @@ std::pair<unsigned, unsigned> pm_selectors(const Module& m) {
   return {s0, s1};
 }
 
+// ---- "pm2": configs whose modules are all plane-major with ONE scan family (same column order, planes MSB first) -------------
+// The first generation of the plane-major path emitted, per module, a scoring function (all 32 residue words) and a winner
+// pass (residues again + statistics + XOR stage + byte transposition): ~70 KiB of straight-line SASS that the instruction
+// cache cannot hold (ncu: a quarter to almost half of the stall samples were instruction fetches), and lanes of a warp that
+// picked different winners each ran a whole winner pass.  Here a module contributes ONE piece of code, its residue pass
+// res_<m> (x -> r[32], before the XOR stage), used both for scoring (it then stops at the first column chunk whose plane 0
+// is set) and for the winner; everything else -- leading-zero-row count, MAE/MSE sums, XOR stage, byte transposition,
+// bit-sliced row classifier -- is emitted once and shared by all modules and all lanes.
+std::vector<std::map<int, uint32_t>> pm_chunks(const Module& m) {
+  std::vector<std::map<int, uint32_t>> chunks(8);
+  for (int j = 0; j < 8; j++)
+    for (int i = 0; i < 16; i++) {
+      const int cidx = m.cols[16 * j + i];
+      chunks[j][cidx / 4] |= 0xFFu << (8 * (cidx % 4));
+    }
+  return chunks;
+}
+
+std::string pm_chunk_or(const std::vector<std::map<int, uint32_t>>& chunks, int j, const char* arr) {
+  // words under the same byte mask are OR-ed first, so that a chunk costs one LOP3 per two words
+  std::vector<std::pair<uint32_t, std::vector<std::string>>> terms;
+  for (auto& wm : chunks[j]) {
+    auto it = std::find_if(terms.begin(), terms.end(), [&](auto& t) { return t.first == wm.second; });
+    if (it == terms.end()) { terms.push_back({wm.second, {}}); it = terms.end() - 1; }
+    it->second.push_back(fmt("%s[%d]", arr, wm.first));
+  }
+  std::vector<std::string> parts;
+  for (auto& t : terms)
+    parts.push_back(t.first != 0xFFFFFFFFu ? fmt("((%s) & 0x%08xu)", join(t.second, " | ").c_str(), t.first) : fmt("(%s)", join(t.second, " | ").c_str()));
+  return join(parts, " | ");
+}
+
+void emit_res_pm2(const Module& m, Lines& out) {
+  out.push_back(fmt("__device__ __forceinline__ uint32_t res_%d(const uint32_t (&x)[32], uint32_t (&r)[32], bool scoring) {", m.idx));
+  const char* eah = getenv("MPC_SPEC_PM2_AH");
+  const bool use_ah = !(eah && eah[0] == '0');
+  if (use_ah) {
+    out.push_back("  uint32_t ah[32];");
+    out.push_back("#pragma unroll");
+    out.push_back("  for (int i = 0; i < 32; i++) ah[i] = x[i] | 0x80808080u;  // only the words a plain-copy predictor uses survive");
+  }
+  const auto chunks = pm_chunks(m);
+  std::set<int> have;
+  for (int j = 0; j < 8; j++) {
+    for (auto& wm : chunks[j])
+      if (!have.count(wm.first)) {
+        out.push_back("  { " + m.residue_stmts(wm.first, "rr", use_ah) + fmt(" r[%d] = rr; }", wm.first));
+        have.insert(wm.first);
+      }
+    // rows 0..7 are plane 0 (bit 7, untouched by the XOR stage) of the column chunks in scan order
+    out.push_back(fmt("  if (scoring && ((%s) & 0x80808080u)) return %du;", pm_chunk_or(chunks, j, "r").c_str(), j));
+  }
+  for (int w = 0; w < W; w++)
+    if (!have.count(w)) out.push_back("  { " + m.residue_stmts(w, "rr", use_ah) + fmt(" r[%d] = rr; }", w));
+  out.push_back("  return 8u;  // plane 0 is zero in every chunk (or not scoring): all 32 residue words are in r");
+  out.push_back("}");
+}
+
+void emit_pm2_shared(const std::vector<Module>& mods, Lines& out) {
+  const Module& m0 = mods[0];
+  const auto chunks = pm_chunks(m0);
+  out.push_back("// leading zero rows from complete residues: planes are scanned MSB first, and while every higher plane is zero, plane b of");
+  out.push_back("// the XOR-ed residue equals plane b of the residue itself (XORModule.cpp:9-20), so the count needs no XOR stage");
+  out.push_back("__device__ __forceinline__ uint32_t pm2_lz(const uint32_t (&r)[32]) {");
+  out.push_back("  uint32_t f[8];");
+  for (int j = 0; j < 8; j++)
+    out.push_back(fmt("  { uint32_t o = %s; o |= o >> 16; o |= o >> 8; f[%d] = o & 0xffu; }", pm_chunk_or(chunks, j, "r").c_str(), j));
+  out.push_back("  return pm_leading_zero_rows(f);");
+  out.push_back("}");
+  out.push_back("");
+  const auto sel = pm_selectors(m0);
+  out.push_back("// residue sums (VPC.cpp:417-443), XOR stage (XORModule.cpp:5-23), scan (ScanModule.cpp:6-22) as a byte transposition into the");
+  out.push_back("// canonical layout of pm_classify, common encoder (FPCModule.cpp:19-158) -- one copy for every module");
+  out.push_back("__device__ __forceinline__ uint32_t pm2_tail(int best, const uint32_t (&x)[32], uint32_t (&r)[32], uint32_t& sa, uint32_t& sq) {");
+  // MAE/MSE run over all line positions: position `root` holds line[root] - predicted[root] there, the residue line holds the root byte
+  out.push_back("  uint32_t rootfix = 0u;");
+  for (auto& m : mods)
+    if (m.root_pred != m.root)
+      out.push_back(fmt("  if (best == %d) rootfix = ((x[%d] >> %d) - (x[%d] >> %d)) & 0xffu;", m.idx, m.root / 4, 8 * (m.root % 4), m.root_pred / 4, 8 * (m.root_pred % 4)));
+  out.push_back("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;");
+  out.push_back("  { const uint32_t rs = (r[0] & 0xffffff00u) | rootfix; sa0 = mpcdev::sum_u8x4_acc(rs, sa0); sq0 = __dp4a(rs, rs, sq0); }");
+  out.push_back("#pragma unroll");
+  out.push_back("  for (int w = 1; w < 32; w++) {");
+  out.push_back("    if ((w & 3) == 0) { sa0 = mpcdev::sum_u8x4_acc(r[w], sa0); sq0 = __dp4a(r[w], r[w], sq0); }");
+  out.push_back("    else if ((w & 3) == 1) { sa1 = mpcdev::sum_u8x4_acc(r[w], sa1); sq1 = __dp4a(r[w], r[w], sq1); }");
+  out.push_back("    else if ((w & 3) == 2) { sa2 = mpcdev::sum_u8x4_acc(r[w], sa2); sq2 = __dp4a(r[w], r[w], sq2); }");
+  out.push_back("    else { sa3 = mpcdev::sum_u8x4_acc(r[w], sa3); sq3 = __dp4a(r[w], r[w], sq3); }");
+  out.push_back("  }");
+  out.push_back("  sa = (sa0 + sa1) + (sa2 + sa3); sq = (sq0 + sq1) + (sq2 + sq3);");
+  bool any_c = false, any_f = false;
+  std::vector<std::string> cmods;
+  for (auto& m : mods) { if (m.cxor) { any_c = true; cmods.push_back(fmt("best == %d", m.idx)); } else any_f = true; }
+  const char* xc_loop = "    r[0] = xc(r[0], 0x7f7f7f00u);\n#pragma unroll\n    for (int w = 1; w < 32; w++) r[w] = xc(r[w], 0x7f7f7f7fu);";
+  const char* xf_loop = "    r[0] = xf(r[0], 0x7f7f7f00u);\n#pragma unroll\n    for (int w = 1; w < 32; w++) r[w] = xf(r[w], 0x7f7f7f7fu);";
+  if (any_c && any_f) {
+    out.push_back("  if (" + join(cmods, " || ") + ") {  // consecutive XOR");
+    out.push_back(xc_loop);
+    out.push_back("  } else {  // first-plane XOR");
+    out.push_back(xf_loop);
+    out.push_back("  }");
+  } else {
+    out.push_back("  {");
+    out.push_back(any_c ? xc_loop : xf_loop);
+    out.push_back("  }");
+  }
+  out.push_back("  uint32_t c[32];");
+  for (int h = 0; h < 2; h++)
+    for (int k = 0; k < 16; k++) {
+      int srcs[4];
+      for (int q = 0; q < 4; q++) srcs[q] = m0.cols[16 * (4 * h + q) + k];
+      out.push_back(fmt("  c[%d] = %s;", 16 * h + k, gather_expr("r", srcs).c_str()));
+    }
+  out.push_back(fmt("  return encode_pm<0x%04xu, 0x%04xu>(c);", sel.first, sel.second));
+  out.push_back("}");
+  out.push_back("");
+}
+
+// Cfg::select_encode for pm2 configs: the per-thread state machine (module k, scoring or winner pass) around ONE switch
+// over the residue passes.  VPC.cpp:372-395: most leading zero rows wins, ties go to the later module -- so the last module
+// wins unscored while no earlier module has a zero row.
+void emit_pm2_select_encode(const std::vector<Module>& mods, Lines& out) {
+  const int first = mods.front().idx, last = mods.back().idx;
+  out.push_back("  __device__ static __forceinline__ uint32_t select_encode(uint32_t (&x)[32], int& best, uint32_t& sa, uint32_t& sq, unsigned lanes) {");
+  out.push_back("    uint32_t r[32];");
+  out.push_back("    uint32_t bestz = 0u;");
+  out.push_back(fmt("    int k = %d;", first));
+  out.push_back(fmt("    bool scoring = %s;", first == last ? "false" : "true"));
+  if (first == last) out.push_back(fmt("    best = %d;", last));
+  out.push_back("    for (;;) {");
+  out.push_back("      // the block does not change between iterations, so the compiler would hoist every predictor gather of every module out of");
+  out.push_back("      // the loop (and spill them); an empty asm per word makes the block opaque at the top of each iteration (no instruction)");
+  out.push_back("#pragma unroll");
+  out.push_back("      for (int i = 0; i < 32; i++) asm volatile(\"\" : \"+r\"(x[i]));");
+  out.push_back("      uint32_t ze = 8u;");
+  out.push_back("      switch (k) {");
+  for (auto& m : mods) out.push_back(fmt("        case %d: ze = res_%d(x, r, scoring); break;", m.idx, m.idx));
+  out.push_back("        default: break;");
+  out.push_back("      }");
+  out.push_back("      if (!scoring) break;");
+  out.push_back("      const uint32_t z = (ze == 8u) ? pm2_lz(r) : ze;");
+  out.push_back("      if (bestz <= z) { best = k; bestz = z; }");
+  out.push_back(fmt("      if (k == %d) {  // every module is scored: r holds the winner's residues only if the last module won with a complete pass", last));
+  out.push_back("        scoring = false;");
+  out.push_back(fmt("        if (best == %d && ze == 8u) break;", last));
+  out.push_back("        k = best;");
+  out.push_back("        continue;");
+  out.push_back("      }");
+  out.push_back("      k++;");
+  out.push_back(fmt("      if (k == %d && bestz == 0u) { best = %d; scoring = false; }  // the last module wins every tie", last, last));
+  out.push_back("    }");
+  out.push_back("    __syncwarp(lanes);  // one pass over the shared tail for the whole warp, whatever modules its lanes picked");
+  out.push_back("    return pm2_tail(best, x, r, sa, sq);");
+  out.push_back("  }");
+}
+
 template <class T>
 std::string int_array(const T* vals, int count, int width) {
   std::string s = "{";
@@ -595,6 +750,13 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   std::string why;
   if (!build_modules(cfg, &mods, &why)) return t;
   bool has_pm = false, has_cm = false, all_c = true, any_c = false;
+  // pm2 (see emit_res_pm2): every module plane-major, planes MSB first, one column order
+  t.pm2 = !mods.empty();
+  for (auto& m : mods) t.pm2 = t.pm2 && m.family == Module::kPm && m.rho_identity() && m.cols == mods[0].cols;
+  {
+    const char* e2 = getenv("MPC_SPEC_PM2");
+    if (e2 && e2[0] == '0') t.pm2 = false;
+  }
   for (auto& m : mods) {
     if (m.family == Module::kPm) has_pm = true;
     else { has_cm = true; all_c = all_c && m.cxor; any_c = any_c || m.cxor; }
@@ -695,10 +857,15 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   for (auto& m : mods) {
     out.push_back(fmt("// ---- module %d: %s, root %d, %s XOR, %s-major scan ----", m.idx, kPredNames[m.predictor], m.root,
                       m.cxor ? "consecutive" : "first-plane", m.family == Module::kCm ? "column" : "plane"));
-    if (m.family == Module::kCm) emit_score_cm(m, out); else emit_score_pm(m, out);
-    emit_full(m, out, t.lut_xor, lay);
+    if (t.pm2) {
+      emit_res_pm2(m, out);
+    } else {
+      if (m.family == Module::kCm) emit_score_cm(m, out); else emit_score_pm(m, out);
+      emit_full(m, out, t.lut_xor, lay);
+    }
     out.push_back("");
   }
+  if (t.pm2) emit_pm2_shared(mods, out);
   out.push_back("struct Cfg {");
   out.push_back(fmt("  static constexpr int kNumModules = %d;", n));
   out.push_back(fmt("  static constexpr int kFirst = %d;", first));
@@ -715,12 +882,22 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
                     t.use_lut ? t.lut_xor : 0));
   out.push_back(fmt("  static constexpr int kMinCtasPerSm = %d;  // __launch_bounds__: register budget 65536 / (threads * CTAs)", t.min_ctas));
   out.push_back(fmt("  static constexpr int kQueueCap = %d;  // entries per regrouping queue (one queue per PredComp module); 0 = no regrouping", t.queue_cap));
+  out.push_back(fmt("  static constexpr bool kPm2 = %s;  // one residue pass per module + shared scoring / statistics / classifier (select_encode)", t.pm2 ? "true" : "false"));
   out.push_back("  __device__ static __forceinline__ uint32_t enc(int k) {  // encoding bits of cluster k-1, VPC.cpp:102-117");
   out.push_back("    switch (k) {");
   for (int k = 0; k <= n; k++) out.push_back(fmt("      case %d: return %du;", k, cfg.enc_bits[k]));
   out.push_back("    }");
   out.push_back("    return 0u;");
   out.push_back("  }");
+  if (t.pm2) {
+    emit_pm2_select_encode(mods, out);
+    out.push_back("  __device__ static __forceinline__ void select(const uint32_t (&)[32], int&, uint32_t&, unsigned) {}");
+    out.push_back("  static constexpr bool kAdaptiveEncode = false;");
+    out.push_back("  __device__ static __forceinline__ uint32_t encode(int, const uint32_t (&)[32], uint32_t&, uint32_t&, unsigned, const uint8_t*, bool) { return 0u; }");
+    out.push_back("};");
+    out.push_back("");
+  } else {
+  out.push_back("  __device__ static __forceinline__ uint32_t select_encode(uint32_t (&)[32], int&, uint32_t&, uint32_t&, unsigned) { return 0u; }");
   out.push_back("  // VPC.cpp:372-395: most leading zero rows wins, ties go to the later module");
   out.push_back("  __device__ static __forceinline__ void select(const uint32_t (&x)[32], int& best, uint32_t& bestz, unsigned lanes) {");
   out.push_back("    uint32_t z;");
@@ -790,6 +967,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   out.push_back("  }");
   out.push_back("};");
   out.push_back("");
+  }  // !pm2
   if (jit) {
     out.push_back(fmt("}  // namespace spec_%s", name.c_str()));
     out.push_back("}  // namespace mpc");
