@@ -204,7 +204,7 @@ struct Module {
           terms.push_back(s ? fmt("((p << %d) & 0x%08xu)", s, m) : fmt("(p & 0x%08xu)", m));
         } else {
           for (int q : kv.second) m |= (uint32_t)(0xFF >> -s) << (8 * q);
-          terms.push_back(fmt("((p >> %d) & 0x%08xu)", -s, m));
+          terms.push_back(fmt("(mpcdev::shr_fma(p, %d) & 0x%08xu)", -s, m));  // the shift on the FMA pipe (IMAD.HI): the kernels are ALU-pipe bound
         }
       }
       if (terms.empty()) return "0u";
