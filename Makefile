@@ -10,7 +10,7 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -I$(CSRC
 CXXFLAGS := -O3 -std=c++17 -fPIC -Iinclude -I$(CSRC) -Wall
 
 LIB      := $(PKG)/libmpc_b200.so
-SPEC_CFGS := P6 F4 Z1 E5
+SPEC_CFGS := P6 F4 Z1 E5 S32 S64
 SPEC_SRCS := $(foreach c,$(SPEC_CFGS),$(CSRC)/spec/spec_$(c).cu)
 CU_SRCS  := $(CSRC)/mpc_capi.cu $(CSRC)/mpc_generic.cu $(CSRC)/mpc_synth.cu $(CSRC)/mpc_variants.cu $(CSRC)/mpc_sc2.cu $(CSRC)/mpc_pattern.cu $(CSRC)/mpc_spec_registry.cu $(CSRC)/mpc_spec_list.cu $(SPEC_SRCS)
 CU_OBJS  := $(CU_SRCS:.cu=.o)

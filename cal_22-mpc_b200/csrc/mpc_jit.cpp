@@ -187,7 +187,8 @@ cudaError_t jit_launch(JitKernel* k, const uint8_t* d_lines, uint64_t n_blocks, 
                        const uint8_t* d_row_lut, uint32_t* d_sched, int sm_count, cudaStream_t stream) {
   if (n_blocks == 0) return cudaSuccess;
   if (n_blocks > 0xffffff00ull) return cudaErrorInvalidValue;  // 32-bit block indices in the kernel: 512 GiB per launch
-  const uint64_t n_tiles = (n_blocks + 31) / 32;
+  const uint64_t tile_lines = 32ull * (uint64_t)(128 / k->traits.line_size);
+  const uint64_t n_tiles = (n_blocks + tile_lines - 1) / tile_lines;
   uint64_t grid = (uint64_t)sm_count * k->per_sm;
   const uint64_t want = (n_tiles + k->traits.warps - 1) / k->traits.warps;
   if (grid > want) grid = want;

@@ -11,7 +11,7 @@
 //     stop at their first non-zero row (VPC.cpp:378-387).
 // The same generator serves the ahead-of-time build (tools/specgen -> csrc/spec/spec_<name>.cu, compiled by nvcc)
 // and the run-time path (mpc_jit.cpp: NVRTC at mpc_create for configs that were not compiled in).
-// Eligible: lineSize 128 and every PredComp scan table column-major or plane-major; everything else stays on the
+// Eligible: lineSize 32 / 64 / 128 and every PredComp scan table column-major or plane-major; everything else stays on the
 // generic warp-per-block kernel.
 #include "mpc_specgen.h"
 
@@ -27,8 +27,13 @@
 namespace mpc {
 namespace {
 
-constexpr int L = 128;
-constexpr int W = 32;
+// Line geometry of the config being compiled (set by build_modules): L bytes = W words per line, R = L / 2 scan rows of 16 bits,
+// NCH = L / 16 column chunks per bit plane.  A thread always holds 128 bytes = 128 / L consecutive lines (mpc_spec.cuh).
+constexpr int kMaxL = 128;
+thread_local int L = 128;
+thread_local int W = 32;
+inline int R() { return L / 2; }
+inline int NCH() { return L / 16; }
 
 std::string fmt(const char* f, ...) {
   char buf[512];
@@ -112,7 +117,7 @@ struct Module {
   int idx = 0;
   int predictor = 0, root = 0;
   bool cxor = false;
-  int xsrc[L], psrc[L], pval[L];
+  int xsrc[kMaxL], psrc[kMaxL], pval[kMaxL];
   enum Op { kNone, kAdd, kShift } op = kNone;
   int root_pred = 0;
   enum Family { kCm, kPm } family = kCm;
@@ -131,7 +136,7 @@ struct Module {
     root = m.root;
     cxor = m.consecutive_xor != 0;
     if (predictor == MPC_PRED_CONSEC && root != 0) { *why = "Consecutive predictor with root != 0"; return false; }
-    int tperm[L], t = 0;
+    int tperm[kMaxL], t = 0;
     for (int plane = 3; plane >= 0; plane--)
       for (int i = plane; i < L; i += 4) tperm[t++] = i;
     // source tables in residue order (same construction as build_generic_tables, mpc_generic.cu)
@@ -261,8 +266,8 @@ struct Module {
 // "run" (words whose ra and rb both advance by one) and shifted into place in the 64-bit zero-row mask at the end.
 struct RowLayout {
   bool paired = false;
-  int ra[W], rb[W];      // rows in the low / high halfword of word j
-  int grp[W], slot[W];   // flag accumulator of word j and its bit position in it
+  int ra[kMaxL / 4], rb[kMaxL / 4];      // rows in the low / high halfword of word j
+  int grp[kMaxL / 4], slot[kMaxL / 4];   // flag accumulator of word j and its bit position in it
   struct Group { int A, B, len; };
   std::vector<Group> groups;
 };
@@ -296,7 +301,7 @@ RowLayout plan_row_layout(const std::vector<std::vector<int>>& cm_cols) {
   };
   // rows that read the same pair of residue words are paired first (in row order), then any two rows that fit one PRMT
   std::map<std::set<int>, std::vector<int>> buckets;
-  for (int r = 0; r < 64; r++) buckets[words_of(r)].push_back(r);
+  for (int r = 0; r < R(); r++) buckets[words_of(r)].push_back(r);
   std::vector<std::pair<int, int>> pairs;
   std::vector<int> left;
   for (auto& kv : buckets) {
@@ -363,7 +368,7 @@ void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay) {
   out.push_back("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one");
   out.push_back("  uint32_t ah[32];");
   out.push_back("#pragma unroll");
-  out.push_back("  for (int i = 0; i < 32; i++) ah[i] = x[i] | 0x80808080u;  // only the words a plain-copy predictor uses survive");
+  out.push_back(fmt("  for (int i = 0; i < %d; i++) ah[i] = x[i] | 0x80808080u;  // only the words a plain-copy predictor uses survive", W));
   for (int w = 0; w < W; w++) {
     out.push_back("  { " + m.residue_stmts(w, "r", true));
     if (w == 0) {
@@ -397,10 +402,10 @@ void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay) {
       out.push_back(fmt("  c[%d] = %s;", j, gather_expr("g", srcs).c_str()));
     }
   } else {
-    for (int h = 0; h < 2; h++)
+    for (int h = 0; h < (NCH() + 3) / 4; h++)
       for (int k = 0; k < 16; k++) {
         int srcs[4];
-        for (int q = 0; q < 4; q++) srcs[q] = m.cols[16 * (4 * h + q) + k];
+        for (int q = 0; q < 4; q++) srcs[q] = (4 * h + q) < NCH() ? m.cols[16 * (4 * h + q) + k] : -1;  // lines of 32 bytes: two chunks, two zero lanes
         out.push_back(fmt("  c[%d] = %s;", 16 * h + k, gather_expr("g", srcs).c_str()));
       }
   }
@@ -422,7 +427,8 @@ void emit_encode_rows(const RowLayout& lay, Lines& out) {
   out.push_back("  uint64_t nzm = 0;");
   for (size_t g = 0; g < lay.groups.size(); g++)
     out.push_back(fmt("  nzm |= ((uint64_t)(n%d & 0xffffu) << %d) | ((uint64_t)(n%d >> 16) << %d);", (int)g, lay.groups[g].A, (int)g, lay.groups[g].B));
-  out.push_back("  return (a0 + a1) + (a2 + a3) + mpcdev::zero_run_cost(~nzm);");
+  if (R() < 64) out.push_back(fmt("  return (a0 + a1) + (a2 + a3) + mpcdev::zero_run_cost(~nzm & 0x%llxull);  // %d rows", (1ull << R()) - 1ull, R()));
+  else out.push_back("  return (a0 + a1) + (a2 + a3) + mpcdev::zero_run_cost(~nzm);");
   out.push_back("}");
   out.push_back("");
 }
@@ -435,14 +441,15 @@ void emit_score_cm(const Module& m, Lines& out) {
   std::set<int> have;
   std::vector<int> cols = m.cols;
   cols.resize(L, -1);
-  std::vector<std::map<int, uint32_t>> tests(64);
-  for (int k = 0; k < 64; k++)
+  const int nrows = R();
+  std::vector<std::map<int, uint32_t>> tests(nrows);
+  for (int k = 0; k < nrows; k++)
     for (int cidx : {cols[2 * k], cols[2 * k + 1]})
       if (cidx >= 0) tests[k][cidx / 4] |= 0xFFu << (8 * (cidx % 4));
-  for (int k = 0; k < 64; k += 2) {
+  for (int k = 0; k < nrows; k += 2) {
     std::vector<int> group;
     for (int kk : {k, k + 1})
-      if (kk < 64 && !tests[kk].empty()) group.push_back(kk);
+      if (kk < nrows && !tests[kk].empty()) group.push_back(kk);
     for (int kk : group)
       for (auto& wm : tests[kk])
         if (!have.count(wm.first)) {
@@ -469,7 +476,7 @@ void emit_score_cm(const Module& m, Lines& out) {
     else if (exprs.size() == 1)
       out.push_back(fmt("  if ((%s) != 0u) return %du;", exprs[0].second.c_str(), exprs[0].first));
   }
-  out.push_back("  return 64u;");
+  out.push_back(fmt("  return %du;", nrows));
   out.push_back("}");
 }
 
@@ -489,8 +496,9 @@ void emit_score_pm(const Module& m, Lines& out) {
   out.push_back(fmt("__device__ __forceinline__ uint32_t score_%d(const uint32_t (&x)[32]) {", m.idx));
   out.push_back("  uint32_t g[32];");
   const bool early = (m.rho[0] == 0);  // plane 0 (bit 7) is untouched by the XOR stage: test it on the residues alone
-  std::vector<std::map<int, uint32_t>> chunks(8);
-  for (int j = 0; j < 8; j++)
+  const int nch = NCH();
+  std::vector<std::map<int, uint32_t>> chunks(nch);
+  for (int j = 0; j < nch; j++)
     for (int i = 0; i < 16; i++) {
       const int cidx = m.cols[16 * j + i];
       chunks[j][cidx / 4] |= 0xFFu << (8 * (cidx % 4));
@@ -506,7 +514,7 @@ void emit_score_pm(const Module& m, Lines& out) {
     // chunks in scan order, computing only the residue words a chunk needs, and stop at the first set bit -- a module
     // that loses on its first rows costs a handful of words instead of the whole line.
     std::set<int> have;
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < nch; j++) {
       for (auto& wm : chunks[j])
         if (!have.count(wm.first)) {
           out.push_back("  { " + m.residue_stmts(wm.first, "r") + fmt(" g[%d] = r; }", wm.first));
@@ -526,9 +534,9 @@ void emit_score_pm(const Module& m, Lines& out) {
     out.push_back("  // plane b of the residue itself (XORModule.cpp:9-20), so the leading-zero count needs no XOR stage");
   }
   out.push_back("  uint32_t f[8];");
-  for (int j = 0; j < 8; j++)
+  for (int j = 0; j < nch; j++)
     out.push_back(fmt("  { uint32_t o = %s; o |= o >> 16; o |= o >> 8; f[%d] = %s; }", chunk_or(j, "g").c_str(), j, plane_order_expr("o", m).c_str()));
-  out.push_back("  return pm_leading_zero_rows(f);");
+  out.push_back(fmt("  return pm_leading_zero_rows<%d>(f);", nch));
   out.push_back("}");
 }
 
@@ -551,8 +559,8 @@ std::pair<unsigned, unsigned> pm_selectors(const Module& m) {
 // is set) and for the winner; everything else -- leading-zero-row count, MAE/MSE sums, XOR stage, byte transposition,
 // bit-sliced row classifier -- is emitted once and shared by all modules and all lanes.
 std::vector<std::map<int, uint32_t>> pm_chunks(const Module& m) {
-  std::vector<std::map<int, uint32_t>> chunks(8);
-  for (int j = 0; j < 8; j++)
+  std::vector<std::map<int, uint32_t>> chunks(NCH());
+  for (int j = 0; j < NCH(); j++)
     for (int i = 0; i < 16; i++) {
       const int cidx = m.cols[16 * j + i];
       chunks[j][cidx / 4] |= 0xFFu << (8 * (cidx % 4));
@@ -581,11 +589,11 @@ void emit_res_pm2(const Module& m, Lines& out) {
   if (use_ah) {
     out.push_back("  uint32_t ah[32];");
     out.push_back("#pragma unroll");
-    out.push_back("  for (int i = 0; i < 32; i++) ah[i] = x[i] | 0x80808080u;  // only the words a plain-copy predictor uses survive");
+    out.push_back(fmt("  for (int i = 0; i < %d; i++) ah[i] = x[i] | 0x80808080u;  // only the words a plain-copy predictor uses survive", W));
   }
   const auto chunks = pm_chunks(m);
   std::set<int> have;
-  for (int j = 0; j < 8; j++) {
+  for (int j = 0; j < NCH(); j++) {
     for (auto& wm : chunks[j])
       if (!have.count(wm.first)) {
         out.push_back("  { " + m.residue_stmts(wm.first, "rr", use_ah) + fmt(" r[%d] = rr; }", wm.first));
@@ -596,7 +604,7 @@ void emit_res_pm2(const Module& m, Lines& out) {
   }
   for (int w = 0; w < W; w++)
     if (!have.count(w)) out.push_back("  { " + m.residue_stmts(w, "rr", use_ah) + fmt(" r[%d] = rr; }", w));
-  out.push_back("  return 8u;  // plane 0 is zero in every chunk (or not scoring): all 32 residue words are in r");
+  out.push_back(fmt("  return %du;  // plane 0 is zero in every chunk (or not scoring): all residue words are in r", NCH()));
   out.push_back("}");
 }
 
@@ -607,9 +615,9 @@ void emit_pm2_shared(const std::vector<Module>& mods, Lines& out) {
   out.push_back("// the XOR-ed residue equals plane b of the residue itself (XORModule.cpp:9-20), so the count needs no XOR stage");
   out.push_back("__device__ __forceinline__ uint32_t pm2_lz(const uint32_t (&r)[32]) {");
   out.push_back("  uint32_t f[8];");
-  for (int j = 0; j < 8; j++)
+  for (int j = 0; j < NCH(); j++)
     out.push_back(fmt("  { uint32_t o = %s; o |= o >> 16; o |= o >> 8; f[%d] = o & 0xffu; }", pm_chunk_or(chunks, j, "r").c_str(), j));
-  out.push_back("  return pm_leading_zero_rows(f);");
+  out.push_back(fmt("  return pm_leading_zero_rows<%d>(f);", NCH()));
   out.push_back("}");
   out.push_back("");
   const auto sel = pm_selectors(m0);
@@ -624,7 +632,7 @@ void emit_pm2_shared(const std::vector<Module>& mods, Lines& out) {
   out.push_back("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;");
   out.push_back("  { const uint32_t rs = (r[0] & 0xffffff00u) | rootfix; sa0 = mpcdev::sum_u8x4_acc(rs, sa0); sq0 = __dp4a(rs, rs, sq0); }");
   out.push_back("#pragma unroll");
-  out.push_back("  for (int w = 1; w < 32; w++) {");
+  out.push_back(fmt("  for (int w = 1; w < %d; w++) {", W));
   out.push_back("    if ((w & 3) == 0) { sa0 = mpcdev::sum_u8x4_acc(r[w], sa0); sq0 = __dp4a(r[w], r[w], sq0); }");
   out.push_back("    else if ((w & 3) == 1) { sa1 = mpcdev::sum_u8x4_acc(r[w], sa1); sq1 = __dp4a(r[w], r[w], sq1); }");
   out.push_back("    else if ((w & 3) == 2) { sa2 = mpcdev::sum_u8x4_acc(r[w], sa2); sq2 = __dp4a(r[w], r[w], sq2); }");
@@ -634,8 +642,10 @@ void emit_pm2_shared(const std::vector<Module>& mods, Lines& out) {
   bool any_c = false, any_f = false;
   std::vector<std::string> cmods;
   for (auto& m : mods) { if (m.cxor) { any_c = true; cmods.push_back(fmt("best == %d", m.idx)); } else any_f = true; }
-  const char* xc_loop = "    r[0] = xc(r[0], 0x7f7f7f00u);\n#pragma unroll\n    for (int w = 1; w < 32; w++) r[w] = xc(r[w], 0x7f7f7f7fu);";
-  const char* xf_loop = "    r[0] = xf(r[0], 0x7f7f7f00u);\n#pragma unroll\n    for (int w = 1; w < 32; w++) r[w] = xf(r[w], 0x7f7f7f7fu);";
+  const std::string xc_loop_s = fmt("    r[0] = xc(r[0], 0x7f7f7f00u);\n#pragma unroll\n    for (int w = 1; w < %d; w++) r[w] = xc(r[w], 0x7f7f7f7fu);", W);
+  const std::string xf_loop_s = fmt("    r[0] = xf(r[0], 0x7f7f7f00u);\n#pragma unroll\n    for (int w = 1; w < %d; w++) r[w] = xf(r[w], 0x7f7f7f7fu);", W);
+  const char* xc_loop = xc_loop_s.c_str();
+  const char* xf_loop = xf_loop_s.c_str();
   if (any_c && any_f) {
     out.push_back("  if (" + join(cmods, " || ") + ") {  // consecutive XOR");
     out.push_back(xc_loop);
@@ -648,13 +658,13 @@ void emit_pm2_shared(const std::vector<Module>& mods, Lines& out) {
     out.push_back("  }");
   }
   out.push_back("  uint32_t c[32];");
-  for (int h = 0; h < 2; h++)
+  for (int h = 0; h < (NCH() + 3) / 4; h++)
     for (int k = 0; k < 16; k++) {
       int srcs[4];
-      for (int q = 0; q < 4; q++) srcs[q] = m0.cols[16 * (4 * h + q) + k];
+      for (int q = 0; q < 4; q++) srcs[q] = (4 * h + q) < NCH() ? m0.cols[16 * (4 * h + q) + k] : -1;
       out.push_back(fmt("  c[%d] = %s;", 16 * h + k, gather_expr("r", srcs).c_str()));
     }
-  out.push_back(fmt("  return encode_pm<0x%04xu, 0x%04xu>(c);", sel.first, sel.second));
+  out.push_back(fmt("  return encode_pm<%d, 0x%04xu, 0x%04xu>(c);", NCH(), sel.first, sel.second));
   out.push_back("}");
   out.push_back("");
 }
@@ -674,18 +684,18 @@ void emit_pm2_select_encode(const std::vector<Module>& mods, Lines& out) {
   out.push_back("      // the block does not change between iterations, so the compiler would hoist every predictor gather of every module out of");
   out.push_back("      // the loop (and spill them); an empty asm per word makes the block opaque at the top of each iteration (no instruction)");
   out.push_back("#pragma unroll");
-  out.push_back("      for (int i = 0; i < 32; i++) asm volatile(\"\" : \"+r\"(x[i]));");
-  out.push_back("      uint32_t ze = 8u;");
+  out.push_back(fmt("      for (int i = 0; i < %d; i++) asm volatile(\"\" : \"+r\"(x[i]));", W));
+  out.push_back(fmt("      uint32_t ze = %du;", NCH()));
   out.push_back("      switch (k) {");
   for (auto& m : mods) out.push_back(fmt("        case %d: ze = res_%d(x, r, scoring); break;", m.idx, m.idx));
   out.push_back("        default: break;");
   out.push_back("      }");
   out.push_back("      if (!scoring) break;");
-  out.push_back("      const uint32_t z = (ze == 8u) ? pm2_lz(r) : ze;");
+  out.push_back(fmt("      const uint32_t z = (ze == %du) ? pm2_lz(r) : ze;", NCH()));
   out.push_back("      if (bestz <= z) { best = k; bestz = z; }");
   out.push_back(fmt("      if (k == %d) {  // every module is scored: r holds the winner's residues only if the last module won with a complete pass", last));
   out.push_back("        scoring = false;");
-  out.push_back(fmt("        if (best == %d && ze == 8u) break;", last));
+  out.push_back(fmt("        if (best == %d && ze == %du) break;", last, NCH()));
   out.push_back("        k = best;");
   out.push_back("        continue;");
   out.push_back("      }");
@@ -716,15 +726,17 @@ std::string pod_initializer(const mpc_config_pod& c) {
     else if (m.kind == MPC_MOD_ALLWORDSAME) mods.push_back("{MPC_MOD_ALLWORDSAME}");
     else
       mods.push_back(fmt("{MPC_MOD_PREDCOMP, %d, %d, %d, %d, ", m.predictor, m.root, m.consecutive_xor, m.table_size) +
-                     int_array(m.base, L, L) + ", " + int_array(m.diff, L, L) + ", " + int_array(m.shift, L, L) + ", " +
-                     int_array(m.scan_row, m.table_size, 8 * L) + ", " + int_array(m.scan_col, m.table_size, 8 * L) + "}");
+                     int_array(m.base, L, kMaxL) + ", " + int_array(m.diff, L, kMaxL) + ", " + int_array(m.shift, L, kMaxL) + ", " +
+                     int_array(m.scan_row, m.table_size, 8 * kMaxL) + ", " + int_array(m.scan_col, m.table_size, 8 * kMaxL) + "}");
   }
   return fmt("{%d, %d, %d, %d, ", c.line_size, c.num_modules, c.has_wordsame, c.first_predcomp) +
          int_array(c.enc_bits, c.num_modules + 1, MPC_MAX_MODULES + 1) + ", {" + join(mods, ",\n   ") + "}}";
 }
 
 bool build_modules(const mpc_config_pod& cfg, std::vector<Module>* mods, std::string* why) {
-  if (cfg.line_size != L) { *why = "lineSize != 128"; return false; }
+  if (cfg.line_size != 32 && cfg.line_size != 64 && cfg.line_size != 128) { *why = "lineSize is not 32, 64 or 128"; return false; }
+  L = cfg.line_size;
+  W = L / 4;
   if (cfg.num_modules < 1 || cfg.num_modules > MPC_MAX_MODULES) { *why = "num_modules out of range"; return false; }
   for (int i = cfg.first_predcomp; i < cfg.num_modules; i++) {
     Module m;
@@ -763,6 +775,7 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   }
   const char* e;
   t.eligible = true;
+  t.line_size = cfg.line_size;
   t.use_lut = has_cm && !((e = getenv("MPC_SPEC_LUT")) && e[0] == '0');
   t.lut_xor = 0;
   if (t.use_lut && !((e = getenv("MPC_SPEC_LUTXOR")) && e[0] == '0')) t.lut_xor = all_c ? 1 : (!any_c ? 2 : 0);
@@ -783,7 +796,7 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   // per-thread reads want, completion on a per-warp mbarrier) instead of 8 cp.async per lane.  Bit-exact, but measured slower on B200
   // (F4 smooth 4 300 -> 4 020 GB/s, random 4 035 -> 3 785; 2.5 points of it are the fence.proxy.async that must order the warp's reads
   // of the stage before the next copy), so cp.async stays the default.
-  t.tma = t.stages == 1 && (e = getenv("MPC_SPEC_TMA")) && e[0] == '1';
+  t.tma = t.stages == 1 && cfg.line_size == 128 && (e = getenv("MPC_SPEC_TMA")) && e[0] == '1';
   t.smem_bytes = (size_t)t.warps * t.stages * 4096 + (t.tma ? (size_t)((t.warps * 8 + 15) / 16) * 16 : 0) + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
                  (t.use_lut ? 65536 : 0);
   // Regrouping queues (mpc_spec.cuh): one queue per PredComp module in the shared memory that is left (227 KiB per CTA on sm_100,
@@ -803,7 +816,7 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
     // divergent lanes do not already share (the per-module residue pass) is ~260 warp instructions per mixed tile, the queue
     // traffic ~300, and warps that run different modules' passes at the same time overflow the 32 KiB instruction cache
     // (F4 mixed 2 524 -> 1 697 GB/s, homogeneous classes -10 %).  They are therefore OFF unless MPC_SPEC_REGROUP=1 asks.
-    if (!((e = getenv("MPC_SPEC_REGROUP")) && e[0] == '1')) cap = 0;
+    if (!((e = getenv("MPC_SPEC_REGROUP")) && e[0] == '1') || cfg.line_size != 128) cap = 0;
     if ((e = getenv("MPC_SPEC_QUEUE_CAP")) && atoi(e) > 0 && atoi(e) % 32 == 0 && atoi(e) <= cap) cap = atoi(e);
     t.queue_cap = cap;
     if (cap > 0) t.smem_bytes += (size_t)nq * cap * 136 + (size_t)nq * 16 + 16 + 128;
@@ -867,6 +880,8 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   }
   if (t.pm2) emit_pm2_shared(mods, out);
   out.push_back("struct Cfg {");
+  out.push_back(fmt("  static constexpr int kLineBytes = %d;  // a thread holds 128 bytes = 128 / kLineBytes consecutive lines", L));
+  out.push_back(fmt("  static constexpr int kWords = %d;", W));
   out.push_back(fmt("  static constexpr int kNumModules = %d;", n));
   out.push_back(fmt("  static constexpr int kFirst = %d;", first));
   out.push_back(fmt("  static constexpr bool kHasWordSame = %s;", cfg.has_wordsame ? "true" : "false"));
@@ -925,8 +940,8 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     if (std::find(fams.begin(), fams.end(), fam_of(m)) == fams.end()) fams.push_back(fam_of(m));
   std::sort(fams.begin(), fams.end());
   auto call = [&](const std::pair<int, std::pair<unsigned, unsigned>>& f) {
-    return f.first == 0 ? std::string(lay.paired ? "encode_rows(c, lut)" : "encode_cm<kUseLut, kSkipZeroGroups>(c, lut)")
-                        : fmt("encode_pm<0x%04xu, 0x%04xu>(c)", f.second.first, f.second.second);
+    return f.first == 0 ? (lay.paired ? std::string("encode_rows(c, lut)") : fmt("encode_cm<%d, kUseLut, kSkipZeroGroups>(c, lut)", W))
+                        : fmt("encode_pm<%d, 0x%04xu, 0x%04xu>(c)", NCH(), f.second.first, f.second.second);
   };
   if (t.adaptive_encode) {
     out.push_back("    if (uniform) {  // every lane of the warp runs the same module: straight from its residue pass into the classifier");

@@ -9,6 +9,7 @@ namespace mpc {
 
 struct SpecTraits {
   bool eligible = false;
+  int line_size = 128;           // bytes per line (32 / 64 / 128); a tile of 4 KiB holds 32 * (128 / line_size) lines
   bool use_lut = false;          // column-major modules: 64 KiB shared-memory row-cost table
   int lut_xor = 0;               // 0 plain table, 1 / 2: consecutive / first-plane XOR stage folded into the table
   int warps = 8;                 // warps per CTA
@@ -23,7 +24,7 @@ struct SpecTraits {
   size_t smem_bytes = 0;         // dynamic shared memory of one CTA
 };
 
-// true when a specialised kernel can be generated for cfg (lineSize 128, every scan column- or plane-major)
+// true when a specialised kernel can be generated for cfg (lineSize 32 / 64 / 128, every scan column- or plane-major)
 bool spec_eligible(const mpc_config_pod& cfg, std::string* why);
 SpecTraits spec_traits(const mpc_config_pod& cfg);
 // jit = false: translation unit for the ahead-of-time build (registers itself as kSpec_<name>);

@@ -67,6 +67,20 @@ def test_synthetic_classes(mpcb, cfg, kind, kernel):
     check_against_oracle(mpcb, m, OracleMPC(cfg_path(cfg)), blocks)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("cfg,L", [("S32", 32), ("S64", 64)])
+@pytest.mark.parametrize("kind", ["smooth_f32", "sparse_i32", "mixed_hashed", "wordsame"])
+def test_short_line_shipped_configs(mpcb, cfg, L, kind, kernel):
+    """32- / 64-byte lines (GPGPU-Sim sectors; the reference takes any lineSize, VPC.cpp:99-101): the same dump bytes cut into
+    shorter lines, on the specialised kernel (four / two lines per thread) and on the generic one; ragged line count"""
+    m = mpcb.Mpc(cfg_path(cfg))
+    m.set_kernel(kernel)
+    if kernel == 0:
+        assert m.kernel_name() == "spec_thread:" + cfg
+    blocks = synth(kind, 77, 999, 1501, 1 << 20).reshape(-1, L)[: 1501 * (128 // L) - 3]
+    check_against_oracle(mpcb, m, OracleMPC(cfg_path(cfg)), blocks)
+
+
 @pytest.mark.parametrize("seed", range(16))
 def test_random_configs(mpcb, seed):
     rng = np.random.default_rng(7000 + seed)

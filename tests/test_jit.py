@@ -1,5 +1,5 @@
 """Run-time specialisation: the config compiler (csrc/mpc_specgen.cpp) + NVRTC build a thread-per-block kernel for any
-config with 128-byte lines and column-/plane-major scan tables.  CPU: the generated sources compile for sm_100a.
+config with 32-, 64- or 128-byte lines and column-/plane-major scan tables.  CPU: the generated sources compile for sm_100a.
 GPU: the kernels are bit-exact against the oracle."""
 import json
 
@@ -10,12 +10,12 @@ from helpers import SHIPPED, cfg_path, random_blocks, random_config
 from oracle.bridge import OracleMPC
 
 
-def eligible_config(seed):
+def eligible_config(seed, L=128):
     rng = np.random.default_rng(seed)
     mode = ["cm", "pm", "pmr", "cms", "cm", "pm"][seed % 6]
-    cfg = random_config(rng, L=128, n_pred=int(rng.integers(1, 5)), table=mode)
+    cfg = random_config(rng, L=L, n_pred=int(rng.integers(1, 5)), table=mode)
     if seed % 4 == 3:  # mixed families in one config
-        other = random_config(rng, L=128, n_pred=1, table="pm" if mode.startswith("cm") else "cm")
+        other = random_config(rng, L=L, n_pred=1, table="pm" if mode.startswith("cm") else "cm")
         first = [k for k in sorted(other["modules"], key=int) if other["modules"][k]["name"] == "PredComp"][0]
         n = cfg["overview"]["num_modules"]
         cfg["modules"][str(n)] = other["modules"][first]
@@ -43,9 +43,63 @@ def test_ineligible_configs_are_reported(mpcb):
     pod = mpcb.load_config(text=json.dumps(random_config(rng, L=128, n_pred=2, table="perm")))
     rc, _, log = mpcb.jit_compile_check(pod)
     assert rc == -2 and "neither column-major nor plane-major" in log
-    pod = mpcb.load_config(text=json.dumps(random_config(rng, L=64, n_pred=2, table="cm")))
-    rc, _, log = mpcb.jit_compile_check(pod)
-    assert rc == -2 and "lineSize" in log
+
+
+def shared_scan_pm_config(seed, L):
+    """Every module plane-major with ONE column order, planes MSB first (the shape of the survey's probe config P6): the
+    state-machine form of the plane-major path (select_encode)."""
+    rng = np.random.default_rng(seed)
+    cfg = random_config(rng, L=L, n_pred=int(rng.integers(1, 5)), table="pm")
+    mods = [m for m in cfg["modules"].values() if m["name"] == "PredComp"]
+    for m in mods[1:]:
+        m["submodules"]["ScanModule"] = mods[0]["submodules"]["ScanModule"]
+    return cfg
+
+
+@pytest.mark.parametrize("L", [32, 64])
+@pytest.mark.parametrize("seed", range(6))
+def test_short_line_configs_compile(mpcb, seed, L):
+    pod = mpcb.load_config(text=json.dumps(eligible_config(seed, L)))
+    rc, nbytes, log = mpcb.jit_compile_check(pod)
+    assert rc == 0 and nbytes > 5000, log
+
+
+@pytest.mark.parametrize("L", [32, 64, 128])
+@pytest.mark.parametrize("seed", range(3))
+def test_shared_scan_plane_major_configs_compile(mpcb, seed, L):
+    pod = mpcb.load_config(text=json.dumps(shared_scan_pm_config(seed, L)))
+    rc, nbytes, log = mpcb.jit_compile_check(pod)
+    assert rc == 0 and nbytes > 5000, log
+
+
+def check_jit_config(mpcb, cfg, seed, L=128, n=3000):
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(cfg)))
+    assert m.kernel_name() == "spec_thread:jit"
+    rng = np.random.default_rng(seed)
+    blocks = random_blocks(rng, n, L)
+    sizes, sels, st = m.compress(blocks)
+    r = OracleMPC(cfg).run(blocks)
+    bad = np.nonzero((sizes != r.sizes) | (sels != r.sels))[0]
+    assert bad.size == 0, (bad[:5], sizes[bad[:5]], r.sizes[bad[:5]], sels[bad[:5]], r.sels[bad[:5]])
+    assert st.CompressedSize == r.CompressedSize and np.array_equal(st.count, r.count)
+    assert np.array_equal(st.res_abs, r.res_abs) and np.array_equal(st.res_sq, r.res_sq)
+    hb = r.hist.shape[1]
+    assert np.array_equal(st.hist[:, :hb], r.hist)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [32, 64])
+@pytest.mark.parametrize("seed", range(12))
+def test_short_line_jit_kernels_match_oracle(mpcb, seed, L):
+    """32- and 64-byte lines on the thread-per-block kernel: four / two lines per thread; ragged count on purpose"""
+    check_jit_config(mpcb, eligible_config(200 + seed, L), seed, L, n=3001 + seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [32, 64, 128])
+@pytest.mark.parametrize("seed", range(4))
+def test_shared_scan_plane_major_jit_kernels_match_oracle(mpcb, seed, L):
+    check_jit_config(mpcb, shared_scan_pm_config(300 + seed, L), seed, L, n=2999)
 
 
 @pytest.mark.gpu

@@ -13,6 +13,8 @@ The reference ships no config (SURVEY.md section 0.4); its schema is what VPC::p
             of a column together; DiffBase stride 4 / stride 8, OneBase, DiffBase stride 1.
   Z1.json   AllZero + one PredComp only (exercises compressLineOnlyAllZero, VPC.cpp:54-70).
   E5.json   explicit encoding_bits list, 5 modules, mixed scans (plane-major and column-major).
+  S32.json  F4's design for 32-byte lines (GPGPU-Sim sector traces, ACCESS_GRAN 32; LoaderGPGPU.cpp) and
+  S64.json  for 64-byte lines: the reference takes any lineSize (VPC.cpp:99-101).
 """
 import json
 import os
@@ -126,14 +128,23 @@ def e5():
         encoding_bits=[2, 1, 3, 4, 2, 5])
 
 
+def with_line_size(n, make):
+    global L
+    keep, L = L, n
+    try:
+        return make()
+    finally:
+        L = keep
+
+
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(__file__), "..", "configs")
     os.makedirs(out, exist_ok=True)
-    for name, cfg in (("P6", p6()), ("F4", f4()), ("Z1", z1()), ("E5", e5())):
+    for name, cfg in (("P6", p6()), ("F4", f4()), ("Z1", z1()), ("E5", e5()), ("S32", with_line_size(32, f4)), ("S64", with_line_size(64, f4))):
         with open(os.path.join(out, name + ".json"), "w") as f:
             json.dump(cfg, f, separators=(",", ":"))
             f.write("\n")
-    print("wrote P6 F4 Z1 E5 to", out)
+    print("wrote P6 F4 Z1 E5 S32 S64 to", out)
 
 
 if __name__ == "__main__":
