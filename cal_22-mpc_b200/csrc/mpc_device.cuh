@@ -22,8 +22,10 @@ typedef unsigned long size_t;
 
 #if defined(__CUDACC__)
 #define MPC_HD __host__ __device__ __forceinline__
+#define MPC_HDM __host__ __device__ __forceinline__  // member functions
 #else
 #define MPC_HD static inline
+#define MPC_HDM inline
 #endif
 
 namespace mpcdev {

@@ -62,7 +62,8 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
     const bool is_rep = valid && rep == 0;    // Pattern::isRepeated(line, 4) == PatternResult::IsAllWordSame
     int sel;
     uint32_t imm;
-    const uint32_t size = mpcvar::pattern_block(x, &sel, &imm);
+    struct { __device__ __forceinline__ bool operator()(bool b) const { return __all_sync(0xffffffffu, b) != 0; } } vote;  // every lane is here
+    const uint32_t size = mpcvar::pattern_block<32>(x, &sel, &imm, vote);
     if (valid && sizes) sizes[blk] = (uint16_t)size;
     if (valid && hashes) hashes[blk] = mpcvar::block_hash64(x);
     // byte histograms (PatternResult::UpdateCountMap): a word-repeating line is 32 copies of its first word

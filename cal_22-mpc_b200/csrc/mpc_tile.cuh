@@ -22,14 +22,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Calls body(x, blk, valid) for every block of the dump, one block per lane per tile; tiles are dealt round-robin
 // to the warps of the grid.  `my_stage` = this warp's 2 x 4 KiB of shared memory.
 template <class Body>
+// `valid_chunks` (16-byte chunks of the dump that exist; 0 = n_blocks * 8) bounds the reads when the last 128-byte unit is
+// partial (lines of 32 / 64 bytes); the missing chunks arrive as zeros.
 __device__ __forceinline__ void for_each_block(const uint4* __restrict__ lines, uint64_t n_blocks, uint4* my_stage,
-                                               int warps_per_cta, Body body) {
+                                               int warps_per_cta, Body body, uint64_t valid_chunks = 0) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(my_stage);
   const uint64_t n_tiles = (n_blocks + kTileBlocks - 1) / kTileBlocks;
   const uint64_t total_warps = (uint64_t)gridDim.x * warps_per_cta;
-  const uint64_t total_chunks = n_blocks * 8;
+  const uint64_t total_chunks = valid_chunks ? valid_chunks : n_blocks * 8;
   // chunk (b, j) of a tile lands in slot b*8 + (j ^ (b & 7)); lane l copies chunks l, l+32, ...: b = 4i + (l >> 3)
   const uint32_t dst_even = stage_addr + (uint32_t)((lane >> 3) * 8 + ((lane & 7) ^ (lane >> 3))) * 16u;
   const uint32_t dst_odd = stage_addr + (uint32_t)((lane >> 3) * 8 + ((lane & 7) ^ (4 + (lane >> 3)))) * 16u;

@@ -18,7 +18,18 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCounters = 16;  // device layout: [0] compressed bits, [1..16] counters
 
-template <int ALG>
+// warp-wide votes for mpcvar::bdi_block_with: every lane calls the maker, the lanes that run the checks vote among themselves
+struct WarpVote {
+  unsigned mask;
+  __device__ __forceinline__ bool operator()(bool b) const { return __all_sync(mask, b) != 0; }
+};
+struct MakeWarpVote {
+  __device__ __forceinline__ WarpVote operator()(bool runs_checks) const { return WarpVote{__ballot_sync(0xffffffffu, runs_checks)}; }
+};
+
+// W = words per line: a thread holds 128 bytes = 32 / W consecutive lines (32-, 64- and 128-byte lines; the reference's
+// models take any line size, BDI.cpp:108-201, FPC.cpp:7-87, BPC.cpp:20-185)
+template <int ALG, int W>
 __global__ void __launch_bounds__(kThreads)
 variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __restrict__ sizes,
                unsigned long long* __restrict__ stats) {
@@ -29,19 +40,28 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long bits = 0;
-  tile::for_each_block(lines, n_blocks, s_stage + warp * tile::kStages * 256, kWarps,
-                       [&](const uint32_t (&x)[32], uint64_t blk, bool valid) {
+  constexpr int S = 32 / W;  // lines per thread
+  // the tile loader works on 128-byte units: n_blocks lines = ceil(n_blocks / S) units, the last one possibly partial
+  tile::for_each_block(lines, (n_blocks + S - 1) / S, s_stage + warp * tile::kStages * 256, kWarps,
+                       [&](const uint32_t (&x128)[32], uint64_t unit, bool) {
+#pragma unroll
+   for (int sub = 0; sub < S; sub++) {
+    uint32_t x[32];
+#pragma unroll
+    for (int i = 0; i < W; i++) x[i] = x128[sub * W + i];
+    const uint64_t blk = unit * S + sub;
+    const bool valid = blk < n_blocks;
     uint32_t size = 0;
     uint64_t packed = 0;  // eight 8-bit counters
     uint32_t extra = 0;
     if (ALG == MPC_ALG_BDI) {
       int st;
-      size = mpcvar::bdi_block(x, &st);
+      size = mpcvar::bdi_block_with<W>(x, &st, MakeWarpVote());
       packed = 1ull << (4 * st);  // nine 4-bit one-hot counters
     } else if (ALG == MPC_ALG_FPC) {
-      size = mpcvar::fpc_block(x, &packed);
+      size = mpcvar::fpc_block<W>(x, &packed);
     } else {
-      size = mpcvar::bpc_block(x, &packed, &extra);
+      size = mpcvar::bpc_block<W>(x, &packed, &extra);
     }
     if (!valid) { size = 0; packed = 0; extra = 0; }
     if (valid && sizes) sizes[blk] = (uint16_t)size;
@@ -64,7 +84,8 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
         if (lane == 0 && c) atomicAdd(&s_cnt[1 + 7], (unsigned long long)c);  // counts[7] = TotalWords
       }
     }
-  });
+   }  // sub-lines
+  }, n_blocks * (uint64_t)(W / 4));
   // per-thread bit totals -> warp -> CTA -> global
   for (int o = 16; o; o >>= 1) bits += __shfl_down_sync(0xffffffffu, bits, o);
   if (lane == 0 && bits) atomicAdd(&s_cnt[0], bits);
@@ -79,22 +100,30 @@ int vfail(int code, const char* what, cudaError_t e) {
   return code;
 }
 
-template <int ALG>
-cudaError_t launch_variant(const uint8_t* d_lines, uint64_t n, uint16_t* d_sizes, unsigned long long* d_stats, int sms,
-                           cudaStream_t s) {
+template <int ALG, int W>
+cudaError_t launch_variant_w(const uint8_t* d_lines, uint64_t n, uint16_t* d_sizes, unsigned long long* d_stats, int sms,
+                             cudaStream_t s) {
   const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
-  cudaError_t e = cudaFuncSetAttribute(variant_kernel<ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(variant_kernel<ALG, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, variant_kernel<ALG>, kThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, variant_kernel<ALG, W>, kThreads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  const uint64_t tiles = (n + tile::kTileBlocks - 1) / tile::kTileBlocks;
+  const uint64_t units = (n + (32 / W) - 1) / (32 / W);  // 128-byte units
+  const uint64_t tiles = (units + tile::kTileBlocks - 1) / tile::kTileBlocks;
   uint64_t grid = (uint64_t)sms * per_sm;
   const uint64_t want = (tiles + kWarps - 1) / kWarps;
   if (grid > want) grid = want;
-  variant_kernel<ALG><<<(unsigned)grid, kThreads, smem, s>>>(reinterpret_cast<const uint4*>(d_lines), n, d_sizes, d_stats);
+  variant_kernel<ALG, W><<<(unsigned)grid, kThreads, smem, s>>>(reinterpret_cast<const uint4*>(d_lines), n, d_sizes, d_stats);
   return cudaGetLastError();
+}
+template <int ALG>
+cudaError_t launch_variant(const uint8_t* d_lines, uint64_t n, uint32_t line_size, uint16_t* d_sizes, unsigned long long* d_stats, int sms,
+                           cudaStream_t s) {
+  if (line_size == 32) return launch_variant_w<ALG, 8>(d_lines, n, d_sizes, d_stats, sms, s);
+  if (line_size == 64) return launch_variant_w<ALG, 16>(d_lines, n, d_sizes, d_stats, sms, s);
+  return launch_variant_w<ALG, 32>(d_lines, n, d_sizes, d_stats, sms, s);
 }
 
 }  // namespace
@@ -120,7 +149,7 @@ extern "C" int mpc_variant_run_device(int alg, int device, const uint8_t* d_line
   using namespace mpc;
   if (!out || (n_blocks && !d_lines)) { g_verr = "null argument"; return MPC_E_ARG; }
   if (alg < MPC_ALG_BDI || alg > MPC_ALG_BPC) { g_verr = "unknown algorithm id"; return MPC_E_ARG; }
-  if (line_size != 128) { g_verr = "the GPU variants are built for 128-byte blocks"; return MPC_E_ARG; }
+  if (line_size != 32 && line_size != 64 && line_size != 128) { g_verr = "line size must be 32, 64 or 128 bytes"; return MPC_E_ARG; }
   if ((uintptr_t)d_lines & 15) { g_verr = "lines must be 16-byte aligned"; return MPC_E_ARG; }
   if (device < 0 || device >= 16) { g_verr = "device index out of range"; return MPC_E_ARG; }
   std::lock_guard<std::mutex> lock(g_vws_mutex);
@@ -138,9 +167,9 @@ extern "C" int mpc_variant_run_device(int alg, int device, const uint8_t* d_line
   if ((e = cudaMemsetAsync(w.d_stats, 0, (1 + kCounters) * sizeof(unsigned long long), 0)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaMemsetAsync", e);
   if ((e = cudaEventRecord(w.e0, 0)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaEventRecord", e);
   if (n_blocks) {
-    if (alg == MPC_ALG_BDI) e = launch_variant<MPC_ALG_BDI>(d_lines, n_blocks, d_sizes, w.d_stats, sms, 0);
-    else if (alg == MPC_ALG_FPC) e = launch_variant<MPC_ALG_FPC>(d_lines, n_blocks, d_sizes, w.d_stats, sms, 0);
-    else e = launch_variant<MPC_ALG_BPC>(d_lines, n_blocks, d_sizes, w.d_stats, sms, 0);
+    if (alg == MPC_ALG_BDI) e = launch_variant<MPC_ALG_BDI>(d_lines, n_blocks, line_size, d_sizes, w.d_stats, sms, 0);
+    else if (alg == MPC_ALG_FPC) e = launch_variant<MPC_ALG_FPC>(d_lines, n_blocks, line_size, d_sizes, w.d_stats, sms, 0);
+    else e = launch_variant<MPC_ALG_BPC>(d_lines, n_blocks, line_size, d_sizes, w.d_stats, sms, 0);
     if (e != cudaSuccess) return vfail(MPC_E_CUDA, "variant kernel launch", e);
   }
   if ((e = cudaEventRecord(w.e1, 0)) != cudaSuccess) return vfail(MPC_E_CUDA, "cudaEventRecord", e);
@@ -162,7 +191,7 @@ extern "C" int mpc_variant_run_host(int alg, int device, const uint8_t* h_lines,
                                     uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms) {
   using namespace mpc;
   if (!out || (n_blocks && !h_lines)) { g_verr = "null argument"; return MPC_E_ARG; }
-  if (line_size != 128) { g_verr = "the GPU variants are built for 128-byte blocks"; return MPC_E_ARG; }
+  if (line_size != 32 && line_size != 64 && line_size != 128) { g_verr = "line size must be 32, 64 or 128 bytes"; return MPC_E_ARG; }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return vfail(MPC_E_CUDA, "cudaSetDevice", e);
   const uint64_t chunk = (256ull << 20) / line_size;

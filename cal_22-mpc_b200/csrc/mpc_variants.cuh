@@ -60,6 +60,7 @@ MPC_HD bool bdi_delta_fits32(uint32_t base, uint32_t v) {
   return v <= base ? d <= 2u * half - 1u : (d + half) <= half - 2u;
 }
 
+// W = words per line (32 / 16 / 8 for lines of 128 / 64 / 32 bytes); a line sits in x[0..W).
 template <int B>
 MPC_HD uint64_t bdi_value(const uint32_t (&x)[32], int i) {  // little-endian chunk, zero-extended (BDI.cpp:127-153)
   if (B == 8) return (uint64_t)x[2 * i] | ((uint64_t)x[2 * i + 1] << 32);
@@ -67,11 +68,15 @@ MPC_HD uint64_t bdi_value(const uint32_t (&x)[32], int i) {  // little-endian ch
   return (x[i >> 1] >> (16 * (i & 1))) & 0xffffu;
 }
 
+// size of a check that fits, whatever the number of immediates: n + 8 (B + (n - 1) D), n = L / B values
+template <int B, int D, int W>
+MPC_HD constexpr uint32_t bdi_fit_size() { return (uint32_t)(4 * W / B) + 8u * (uint32_t)(B - D + (4 * W / B) * D); }
+
 // BDI::checkBDI, BDI.cpp:108-201: immediates (values that fit D bytes on their own), the first other value is the
 // base, every later one must be within a D-byte delta of it.
-template <int B, int D>
+template <int B, int D, int W = 32>
 MPC_HD uint32_t bdi_check(const uint32_t (&x)[32], uint32_t* imm_out = nullptr) {
-  constexpr int n = 128 / B;
+  constexpr int n = 4 * W / B;
   uint32_t imm = 0;
   bool not_all = false;
   if (B == 8) {
@@ -125,31 +130,150 @@ MPC_HD uint32_t bdi_check(const uint32_t (&x)[32], uint32_t* imm_out = nullptr) 
   return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)B + ((uint32_t)n - imm - 1u) * (uint32_t)D));  // wraps when imm == n
 }
 
+// ---- the common case in one pass per base size ------------------------------------------------------------------------
+// Most of a dump (floats, pointers, noise) holds NO immediate for any delta size of a base size: then the base is value 0,
+// a check either fits -- every value within a D-byte delta of value 0 -- or costs more than the raw line (n + 8 L bits), and
+// the three (two, one) delta sizes of the base size are decided together by the widest delta.  bdi_no_imm<B> proves "no
+// immediate" with one test per value that is sufficient for every delta size; bdi_need<B> returns the smallest delta size
+// (1, 2, 4) that fits all deltas against value 0, or 9.  Lines with immediates take bdi_check.
+// FROM..TO = range of words looked at (the callers vote on the first few words before paying for the whole line)
+template <int B, int FROM, int TO>
+MPC_HD bool bdi_no_imm(const uint32_t (&x)[32]) {
+  bool none = true;
+  if (B == 8) {
+    // an 8-byte value is an immediate for some D <= 4 only if its upper word is 0 or all ones (bdi_fits64<4>)
+#pragma unroll
+    for (int i = FROM / 2; i < TO / 2; i++) none = none && (x[2 * i + 1] + 1u) > 1u;
+  } else if (B == 4) {
+#pragma unroll
+    for (int i = FROM; i < TO; i++) none = none && x[i] > 0xffffu;   // zero-extended: immediate iff v <= 0xff / 0xffff
+  } else {
+#pragma unroll
+    for (int i = FROM; i < TO; i++) none = none && mpcdev::min_u16x2(x[i] & 0xff00ff00u, 0x00010001u) == 0x00010001u;  // both halfwords > 0xff
+  }
+  return none;
+}
+
+// Which form a base size takes is decided per WARP on the GPU: lanes that took different forms would run both, one after
+// the other, and a finely mixed dump would pay for the sum.  `vote(b)` is "b holds for every lane that runs the checks"
+// (__all_sync over those lanes in the kernels, the identity on the host).  The first vote looks at four words only, so that
+// a mixed warp is sent to the general form for a handful of instructions.
+struct BdiSelfVote {
+  MPC_HDM bool operator()(bool b) const { return b; }
+};
+template <int B, int W, class Vote>
+MPC_HD bool bdi_fast_form(const uint32_t (&x)[32], const Vote& vote) {
+  if (!vote(bdi_no_imm<B, 0, 4>(x))) return false;
+  return vote(bdi_no_imm<B, 4, W>(x));
+}
+
+template <int B, int W>
+MPC_HD int bdi_need(const uint32_t (&x)[32]) {
+  constexpr int n = 4 * W / B;
+  if (B == 8) {
+    const uint64_t base = bdi_value<8>(x, 0);
+    bool ok4 = true;
+#pragma unroll
+    for (int g = 0; g < n; g += 4) {
+      if (ok4) {
+#pragma unroll
+        for (int i = g; i < g + 4; i++) ok4 = ok4 && bdi_fits64<4>(base - bdi_value<8>(x, i));
+      }
+    }
+    if (!ok4) return 9;
+    bool ok2 = true, ok1 = true;
+#pragma unroll
+    for (int i = 1; i < n; i++) {
+      const uint64_t d = base - bdi_value<8>(x, i);
+      ok2 = ok2 && bdi_fits64<2>(d);
+      ok1 = ok1 && bdi_fits64<1>(d);
+    }
+    return ok1 ? 1 : (ok2 ? 2 : 4);
+  } else {
+    const uint32_t base = (uint32_t)bdi_value<B>(x, 0);
+    constexpr int DM = B == 4 ? 2 : 1;  // widest delta of this base size
+    bool okw = true;
+#pragma unroll
+    for (int g = 0; g < n; g += 8) {
+      if (okw) {
+#pragma unroll
+        for (int i = g; i < g + 8; i++) okw = okw && bdi_delta_fits32<DM>(base, (uint32_t)bdi_value<B>(x, i));
+      }
+    }
+    if (!okw) return 9;
+    if (B == 2) return 1;
+    bool ok1 = true;
+#pragma unroll
+    for (int i = 1; i < n; i++) ok1 = ok1 && bdi_delta_fits32<1>(base, (uint32_t)bdi_value<B>(x, i));
+    return ok1 ? 1 : 2;
+  }
+}
+
+// The six checks in the reference's order (BDI.cpp:30-66, Pattern.cpp:20-60); a later check only replaces an earlier one when
+// strictly smaller.  A check either fits -- then its size is the constant bdi_fit_size whatever the number of immediates --
+// or costs more than that, so a check whose fitting size cannot beat the best so far is skipped.  Returns the best size
+// (raw = 8 L when nothing beats it); *sel = index 0..5 of the winning check (unchanged when none), *imm = its immediates.
+template <int W, class Vote>
+MPC_HD uint32_t bdi_best_check(const uint32_t (&x)[32], int* sel, uint32_t* imm, const Vote& vote) {
+  uint32_t best = 32u * W, cur, im = 0;
+  // all votes up front: every lane that runs the checks is here (further down lanes skip checks that cannot win)
+  const bool fast8 = bdi_fast_form<8, W>(x, vote), fast4 = bdi_fast_form<4, W>(x, vote), fast2 = bdi_fast_form<2, W>(x, vote);
+  if (fast8) {
+    const int need = bdi_need<8, W>(x);
+    if (need == 1) { best = bdi_fit_size<8, 1, W>(); *sel = 0; *imm = 0; }
+    else if (need == 2 && best > bdi_fit_size<8, 2, W>()) { best = bdi_fit_size<8, 2, W>(); *sel = 1; *imm = 0; }
+    else if (need == 4 && best > bdi_fit_size<8, 4, W>()) { best = bdi_fit_size<8, 4, W>(); *sel = 2; *imm = 0; }
+  } else {
+    cur = bdi_check<8, 1, W>(x, &im); if (best > cur) { best = cur; *sel = 0; *imm = im; }
+    if (best > bdi_fit_size<8, 2, W>()) { cur = bdi_check<8, 2, W>(x, &im); if (best > cur) { best = cur; *sel = 1; *imm = im; } }
+    if (best > bdi_fit_size<8, 4, W>()) { cur = bdi_check<8, 4, W>(x, &im); if (best > cur) { best = cur; *sel = 2; *imm = im; } }
+  }
+  if (best > bdi_fit_size<4, 1, W>()) {
+    if (fast4) {
+      const int need = bdi_need<4, W>(x);
+      if (need == 1) { best = bdi_fit_size<4, 1, W>(); *sel = 3; *imm = 0; }
+      else if (need == 2 && best > bdi_fit_size<4, 2, W>()) { best = bdi_fit_size<4, 2, W>(); *sel = 4; *imm = 0; }
+    } else {
+      cur = bdi_check<4, 1, W>(x, &im); if (best > cur) { best = cur; *sel = 3; *imm = im; }
+      if (best > bdi_fit_size<4, 2, W>()) { cur = bdi_check<4, 2, W>(x, &im); if (best > cur) { best = cur; *sel = 4; *imm = im; } }
+    }
+  }
+  if (best > bdi_fit_size<2, 1, W>()) {
+    if (fast2) {
+      if (bdi_need<2, W>(x) == 1) { best = bdi_fit_size<2, 1, W>(); *sel = 5; *imm = 0; }
+    } else {
+      cur = bdi_check<2, 1, W>(x, &im); if (best > cur) { best = cur; *sel = 5; *imm = im; }
+    }
+  }
+  return best;
+}
+
 // BDI::CompressLine, BDI.cpp:6-74.  Returns bits incl. the 4 encoding bits; *state = BDIState (BDI.h:10-21).
-MPC_HD uint32_t bdi_block(const uint32_t (&x)[32], int* state) {
+// make_vote(runs_checks) is called by every lane of the warp and returns the Vote over the lanes that run the checks
+template <int W, class MakeVote>
+MPC_HD uint32_t bdi_block_with(const uint32_t (&x)[32], int* state, const MakeVote& make_vote) {
   uint32_t any = 0, rep = 0;
 #pragma unroll
-  for (int i = 0; i < 32; i++) { any |= x[i]; rep |= x[i] ^ x[i & 1]; }
-  uint32_t best = 1024u;
+  for (int i = 0; i < W; i++) { any |= x[i]; rep |= x[i] ^ x[i & 1]; }
+  uint32_t best = 32u * W;
   int sel = 8;
+  const auto vote = make_vote(any != 0 && rep != 0);
   if (any == 0) { best = 8; sel = 0; }
   else if (rep == 0) { best = 64; sel = 1; }
   else {
-    // A check either fits -- then its size is the constant n + 8 (B - D + n D) whatever the number of immediates -- or
-    // costs more than that, and a later check only replaces an earlier one when strictly smaller (BDI.cpp:30-66): a
-    // check whose fitting size cannot beat the best so far is skipped.
-    uint32_t cur;
-    cur = bdi_check<8, 1>(x); if (best > cur) { best = cur; sel = 2; }                       // fits: 200
-    if (best > 320u) { cur = bdi_check<8, 2>(x); if (best > cur) { best = cur; sel = 3; } }  // fits: 320
-    if (best > 560u) { cur = bdi_check<8, 4>(x); if (best > cur) { best = cur; sel = 4; } }  // fits: 560
-    if (best > 312u) { cur = bdi_check<4, 1>(x); if (best > cur) { best = cur; sel = 5; } }  // fits: 312
-    if (best > 560u) { cur = bdi_check<4, 2>(x); if (best > cur) { best = cur; sel = 6; } }  // fits: 560
-    if (best > 584u) { cur = bdi_check<2, 1>(x); if (best > cur) { best = cur; sel = 7; } }  // fits: 584
-    if (best == 1024u) sel = 8;
+    int k = -1;
+    uint32_t imm = 0;
+    best = bdi_best_check<W>(x, &k, &imm, vote);
+    sel = (k < 0 || best == 32u * W) ? 8 : 2 + k;
   }
   *state = sel;
   return best + 4u;
 }
+struct BdiMakeSelfVote {
+  MPC_HDM BdiSelfVote operator()(bool) const { return BdiSelfVote(); }
+};
+template <int W = 32>
+MPC_HD uint32_t bdi_block(const uint32_t (&x)[32], int* state) { return bdi_block_with<W>(x, state, BdiMakeSelfVote()); }
 
 // ---- PATTERN (analysis tool) --------------------------------------------------------------------------------------
 // Pattern::CompressLine, Pattern.cpp:6-75: the six base-delta checks in order (checkPattern, Pattern.cpp:109-199, is
@@ -157,19 +281,14 @@ MPC_HD uint32_t bdi_block(const uint32_t (&x)[32], int* state) {
 // (NotDefined) when nothing beats the raw size; *imm = immediates of the selected check (countPattern,
 // Pattern.cpp:201-320: every immediate adds baseSize implicit bytes, every other value baseSize explicit bytes).
 // Returns bits incl. the 4 encoding bits.
-MPC_HD uint32_t pattern_block(const uint32_t (&x)[32], int* sel_out, uint32_t* imm_out) {
-  uint32_t best = 1024u, cur, im = 0, imm = 0;
-  int sel = 9;
-  // as in bdi_block: a check that fits has a constant size, so one that cannot beat the best so far is skipped
-  cur = bdi_check<8, 1>(x, &im); if (best > cur) { best = cur; sel = 0; imm = im; }
-  if (best > 320u) { cur = bdi_check<8, 2>(x, &im); if (best > cur) { best = cur; sel = 1; imm = im; } }
-  if (best > 560u) { cur = bdi_check<8, 4>(x, &im); if (best > cur) { best = cur; sel = 2; imm = im; } }
-  if (best > 312u) { cur = bdi_check<4, 1>(x, &im); if (best > cur) { best = cur; sel = 3; imm = im; } }
-  if (best > 560u) { cur = bdi_check<4, 2>(x, &im); if (best > cur) { best = cur; sel = 4; imm = im; } }
-  if (best > 584u) { cur = bdi_check<2, 1>(x, &im); if (best > cur) { best = cur; sel = 5; imm = im; } }
-  if (best == 1024u) sel = 9;
-  *sel_out = sel;
-  *imm_out = imm;
+template <int W = 32, class Vote = BdiSelfVote>
+MPC_HD uint32_t pattern_block(const uint32_t (&x)[32], int* sel_out, uint32_t* imm_out, const Vote& vote = Vote()) {
+  int k = -1;
+  uint32_t imm = 0;
+  const uint32_t best = bdi_best_check<W>(x, &k, &imm, vote);
+  const bool none = k < 0 || best == 32u * W;
+  *sel_out = none ? 9 : k;
+  *imm_out = none ? 0u : imm;
   return best + 4u;
 }
 
@@ -189,12 +308,13 @@ MPC_HD uint64_t block_hash64(const uint32_t (&x)[32]) {
 // ---- FPC ------------------------------------------------------------------------------------------------------
 // FPC::CompressLine, FPC.cpp:7-87.  counts8 packs the eight per-word prefix counters, 8 bits each (<= 32 per block).
 // The reference's unbounded zero-run scan (FPC.cpp:26) is bounded at the block end here.
+template <int W = 32>
 MPC_HD uint32_t fpc_block(const uint32_t (&x)[32], uint64_t* counts8) {
   uint32_t size = 0;
   uint64_t cnt = 0;
   bool prev_zero = false;
 #pragma unroll
-  for (int i = 0; i < 32; i++) {
+  for (int i = 0; i < W; i++) {
     const uint32_t v = x[i];
     int p;
     uint32_t c;
@@ -232,15 +352,17 @@ MPC_HD void transpose32(uint32_t (&a)[32]) {
 
 // BPC::CompressLine, BPC.cpp:20-87 + encodeFirst (always 7, BPC.cpp:89-101) + encodeDeltas (BPC.cpp:103-185).
 // pat8 packs the 7 pattern counters (BPC.h:13-22), 8 bits each; *words = value added to TotalWords.
+template <int W = 32>
 MPC_HD uint32_t bpc_block(const uint32_t (&x)[32], uint64_t* pat8, uint32_t* words) {
   uint32_t d[32];
   uint32_t neg = 0;  // bit r = delta r negative = bit 32 of the 33-bit delta (words are zero-extended, BPC.cpp:41-45)
 #pragma unroll
-  for (int r = 0; r < 31; r++) {
+  for (int r = 0; r < W - 1; r++) {
     d[r] = x[r + 1] - x[r];
     neg |= (x[r + 1] < x[r] ? 1u : 0u) << r;
   }
-  d[31] = 0;
+#pragma unroll
+  for (int r = W - 1; r < 32; r++) d[r] = 0;  // a line of W words has W - 1 deltas: the planes are W - 1 bits wide
   transpose32(d);  // d[c] = delta bit plane c (bit r = delta r)
   uint32_t length = 7, run = 0, nwords = 0;
   uint64_t pat = 0;

@@ -45,6 +45,35 @@ extern "C" void t_variant_run(int alg, const unsigned char* lines, unsigned long
   }
 }
 
+// the same for lines of W words (32- / 64-byte lines)
+template <int W>
+static void variant_run_w(int alg, const unsigned char* lines, unsigned long long n, unsigned* sizes, unsigned long long* counts) {
+  for (unsigned long long i = 0; i < n; i++) {
+    uint32_t x[32] = {0};
+    __builtin_memcpy(x, lines + i * 4 * W, 4 * W);
+    if (alg == 1) {
+      int st;
+      sizes[i] = mpcvar::bdi_block<W>(x, &st);
+      counts[st]++;
+    } else if (alg == 2) {
+      uint64_t c8;
+      sizes[i] = mpcvar::fpc_block<W>(x, &c8);
+      for (int p = 0; p < 8; p++) counts[p] += (c8 >> (8 * p)) & 0xff;
+    } else {
+      uint64_t p8;
+      uint32_t w;
+      sizes[i] = mpcvar::bpc_block<W>(x, &p8, &w);
+      for (int p = 0; p < 7; p++) counts[p] += (p8 >> (8 * p)) & 0xff;
+      counts[7] += w;
+    }
+  }
+}
+extern "C" void t_variant_run_l(int alg, const unsigned char* lines, unsigned long long n, unsigned L, unsigned* sizes, unsigned long long* counts) {
+  if (L == 32) variant_run_w<8>(alg, lines, n, sizes, counts);
+  else if (L == 64) variant_run_w<16>(alg, lines, n, sizes, counts);
+  else variant_run_w<32>(alg, lines, n, sizes, counts);
+}
+
 // BDI closed-form range tests vs the written-down reduceSign rule (BDI.cpp:203-218)
 extern "C" int t_bdi_fits(unsigned long long x, int D) {
   return D == 1 ? mpcvar::bdi_fits64<1>(x) : D == 2 ? mpcvar::bdi_fits64<2>(x) : mpcvar::bdi_fits64<4>(x);

@@ -136,6 +136,25 @@ def test_bdi_range_tests_equal_the_reduce_sign_rule(swar):
                     assert swar.t_bdi_delta32(base, v, D) == swar.t_bdi_fits_rule((base - v) & M, D), (base, v, D)
 
 
+@pytest.mark.parametrize("alg", ["BDI", "FPC", "BPC"])
+@pytest.mark.parametrize("L", [32, 64, 128])
+def test_variant_block_functions_for_every_line_size(swar, alg, L):
+    """the W-word forms the GPU runs for 32- / 64- / 128-byte lines vs the C oracle (pinned to the reference at all three sizes)"""
+    from helpers import random_blocks
+    from oracle.bridge import VARIANT_ID, oracle_variant
+    from tools.gen_dump import synth
+    rng = np.random.default_rng(L + 1)
+    d = np.concatenate([synth("mixed_hashed", 4, 0, 3000, 3000).reshape(-1, L), random_blocks(rng, 4000, L)])
+    want_sizes, want_counts = oracle_variant(alg, d, L)
+    sizes = np.zeros(d.shape[0], np.uint32)
+    counts = np.zeros(16, np.uint64)
+    swar.t_variant_run_l.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p]
+    swar.t_variant_run_l(VARIANT_ID[alg], d.ctypes.data, d.shape[0], L, sizes.ctypes.data, counts.ctypes.data)
+    bad = np.nonzero(sizes != want_sizes)[0]
+    assert bad.size == 0, (bad[:5], sizes[bad[:5]], want_sizes[bad[:5]])
+    assert np.array_equal(counts, want_counts)
+
+
 def test_bdi_blocks_on_delta_boundaries_match_oracle(swar):
     """Blocks whose values sit on the immediate / delta limits of every (base size, delta size) pair."""
     from oracle.bridge import oracle_variant

@@ -45,6 +45,24 @@ def test_oracle_matches_reference(alg, L):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("alg", ALGS)
+@pytest.mark.parametrize("L", [32, 64])
+def test_gpu_short_lines(mpcb, alg, L):
+    """32- / 64-byte lines (GPGPU-Sim sectors): four / two lines per thread; ragged counts so that the last 128-byte unit is partial"""
+    rng = np.random.default_rng(L)
+    for n in (1, 3, 5, 4099):
+        d = random_blocks(rng, n, L)
+        if n > 1000:
+            d = np.concatenate([d, synth("mixed_hashed", 5, 0, 3000, 3000).reshape(-1, L)[:-1]])
+        sizes, st, _ = mpcb.variant_run(alg, d, line_size=L)
+        want, counts = oracle_variant(alg, d, L)
+        assert np.array_equal(sizes.astype(np.uint32), want), n
+        assert st.blocks == d.shape[0] and st.original_bits == d.shape[0] * 8 * L
+        assert st.compressed_bits == int(want.astype(np.uint64).sum())
+        assert np.array_equal(np.array(st.counts[:9], dtype=np.uint64), counts[:9]), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ALGS)
 def test_gpu_known_answers_and_classes(mpcb, alg):
     sizes, st, _ = mpcb.variant_run(alg, kat_blocks())
     assert sizes.tolist() == KAT[alg]
