@@ -15,7 +15,9 @@ delta-friendly)", compressed with configs/F4.json.
 
 Beside the headline the line carries (unless --no-extras): `parity` (a seeded window of every rank's shard checked
 against the CPU oracle + totals = sum over ranks), `sustained` (the same launch back to back for >= 2 s with clocks),
-`configs.mixed4g` (BASELINE configs[2]: 4 GiB mixed dump, F4 and P6), `configs.dump64g` (configs[3]: the 64 GiB dump,
+`configs.mixed4g` (BASELINE configs[2]: 4 GiB mixed dump, F4 and P6; `configs.mixed4g_by_region` = the same classes laid out
+by region, MPC and BDI / FPC / BPC), `configs.short_lines` (32- / 64-byte lines under S32 / S64: specialised vs generic
+kernel), `configs.dump64g` (configs[3]: the 64 GiB dump,
 sharded over the N GPUs), `configs.variants` (configs[4]: BDI / FPC / BPC / SC2 over the mixed dump with the reference's
 CPU rate beside each), `e2e` with the plain host->device copy ceiling of the same run, and `e2e_file` (an .npy in the
 page cache through bin/compressor).
@@ -535,7 +537,65 @@ def run_mixed4g(job, line):
     line.setdefault("configs", {})["mixed4g"] = out
     if a.variants:
         line["configs"]["variants"] = run_variants(job, d, n)
+    # the same eight classes laid out by region (a dump of arrays: every warp sees one class) -- the other end of the range
+    byreg = {"workload": "the same classes by region ('mixed_regions': class = position in the dump), same size and seed"}
+    m = job.context("F4")
+    m.synth_device(d.data_ptr(), rank * n, n, n * world, "mixed_regions", 31337)
+    m.close()
+    for cfg in ("F4", "P6"):
+        m = job.context(cfg)
+        reps = 5
+        _, k = job.timed_launches(m, d.data_ptr(), n, packed.data_ptr(), reps)
+        parity, red = job.parity_window(m, cfg, d, packed, n, reps)
+        byreg[cfg] = {"value": world * reps * n * BLOCK / (k * 1e-3) / 1e9, "unit": "GB/s", "frac": (n * (BLOCK + 2) / (k / reps * 1e-3) / 1e9) / job.peak,
+                      "comp_ratio": red.CompRatio, "parity": {k2: parity[k2] for k2 in ("blocks_checked", "mismatches", "reduced_totals_equal_sum_over_ranks")}}
+        m.close()
+    if a.variants:
+        for alg in ("BDI", "FPC", "BPC"):
+            for _ in range(2):
+                _, vs, ms = job.mpcb.variant_run(alg, device_ptr=d.data_ptr(), n_blocks=n, device=job.local)
+            ms = job.max_over_ranks(ms)
+            byreg[alg] = {"value": world * n * BLOCK / (ms * 1e-3) / 1e9, "unit": "GB/s", "frac": (n * BLOCK / (ms * 1e-3) / 1e9) / job.peak}
+    line["configs"]["mixed4g_by_region"] = byreg
+    run_short_lines(job, line, d, packed)
     del d, packed
+
+
+def run_short_lines(job, line, d, packed):
+    """32- and 64-byte lines (GPGPU-Sim sectors; the reference takes any lineSize, VPC.cpp:99-101): one GiB of the
+    hash-mixed dump cut into shorter lines under configs S32 / S64, specialised kernel (four / two lines per thread) and
+    the generic warp-per-block kernel beside it, a seeded window of each against the CPU oracle."""
+    from oracle.bridge import OracleMPC
+    torch = job.torch
+    nbytes = min(GIB, d.numel())
+    out = {"workload": f"{nbytes / GIB:g} GiB per GPU of 'mixed_hashed' 128-byte blocks read as 32- / 64-byte lines, per-line output on"}
+    m = job.context("F4")
+    m.synth_device(d.data_ptr(), job.rank * (nbytes // BLOCK), nbytes // BLOCK, job.world * (nbytes // BLOCK), "mixed_hashed", 31337)
+    m.close()
+    for cfg, L in (("S32", 32), ("S64", 64)):
+        n = nbytes // L
+        pk = torch.zeros(n, dtype=torch.int16, device="cuda")
+        row = {}
+        for label, kern, reps in (("spec", 0, 5), ("generic", 1, 1)):
+            m = job.context(cfg)
+            if kern:
+                m.set_kernel(kern)
+            nn = n if not kern else n // 16  # the generic kernel is ~100x slower: a sixteenth of the lines
+            _, k = job.timed_launches(m, d.data_ptr(), nn, pk.data_ptr(), reps, warm=1)
+            row[label] = {"value": job.world * reps * nn * L / (k * 1e-3) / 1e9, "unit": "GB/s", "kernel": m.kernel_name()}
+            if not kern:
+                row[label]["frac"] = (nn * (L + 2) / (k / reps * 1e-3) / 1e9) / job.peak
+                wn = 65536
+                w0 = (n // 3) // wn * wn
+                lines_h = d[w0 * L:(w0 + wn) * L].cpu().numpy().reshape(-1, L)
+                got_sizes, got_sels = job.mpcb.unpack(pk[w0:w0 + wn].cpu().numpy().view(np.uint16))
+                r = OracleMPC(job.cfg_path(cfg)).run(lines_h)
+                mism = int(np.count_nonzero((got_sizes != r.sizes) | (got_sels != r.sels)))
+                row["parity"] = {"lines_checked": wn * job.world, "mismatches": int(job.sum_over_ranks([mism])[0])}
+            m.close()
+        out[cfg] = row
+        del pk
+    line["configs"]["short_lines"] = out
 
 
 def run_variants(job, d, n):
