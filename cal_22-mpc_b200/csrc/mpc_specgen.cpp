@@ -120,8 +120,9 @@ struct Module {
   int xsrc[kMaxL], psrc[kMaxL], pval[kMaxL];
   enum Op { kNone, kAdd, kShift } op = kNone;
   int root_pred = 0;
-  enum Family { kCm, kPm } family = kCm;
+  enum Family { kCm, kPm, kBg } family = kCm;
   std::vector<int> cols;  // scan order (cm: one entry per column group; pm: the 128 columns of a plane group)
+  std::vector<int> bits;  // bg (any other table): scan position i reads bit bits[i] of the XOR-ed residue line seen as W little-endian words
   int rho[8] = {0, 1, 2, 3, 4, 5, 6, 7};  // pm: plane scanned by plane group p
 
   bool rho_identity() const {
@@ -181,8 +182,23 @@ struct Module {
       cols.assign(cs, cs + L);
       return true;
     }
-    *why = fmt("module %d: scan table is neither column-major nor plane-major", idx);
-    return false;
+    // Any other table (ScanModule.cpp:6-22 takes arbitrary (row, column) pairs, duplicates and short tables included): the
+    // "bit-gather" family -- every scan row is assembled from its 16 source bits with shift-and-mask pairs, bits that share a
+    // source word and a shift distance in one pair.  MPC_SPEC_BITGATHER=0 leaves such configs to the generic kernel.
+    {
+      const char* e = getenv("MPC_SPEC_BITGATHER");
+      if (e && e[0] == '0') {
+        *why = fmt("module %d: scan table is neither column-major nor plane-major", idx);
+        return false;
+      }
+    }
+    if (T < 0 || T > 8 * L) { *why = fmt("module %d: scan table larger than the line", idx); return false; }
+    family = kBg;
+    for (int i = 0; i < T; i++) {
+      if (rows[i] > 7 || cs[i] >= L) { *why = fmt("module %d: scan entry outside the line", idx); return false; }
+      bits.push_back(32 * (cs[i] / 4) + 8 * (cs[i] % 4) + 7 - rows[i]);
+    }
+    return true;
   }
 
   // ---- expressions ----
@@ -356,6 +372,7 @@ RowLayout plan_row_layout(const std::vector<std::vector<int>>& cm_cols) {
 
 // encode_rows: the row classifier for the paired layout (row-cost table in shared memory), emitted per config
 void emit_encode_rows(const RowLayout& lay, Lines& out);
+std::string bg_row_pair_expr(const Module& m, int ra, int rb);
 
 // full_<m>: all 32 residue words -> residue sums, canonical row layout c[32].
 // lut_xor != 0 (column-major modules only): the row-cost table is indexed with the residue bytes BEFORE the XOR stage --
@@ -401,6 +418,8 @@ void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay) {
       row_pair_srcs(cols, lay.ra[j], lay.rb[j], srcs);  // legacy layout: rows 2j, 2j+1
       out.push_back(fmt("  c[%d] = %s;", j, gather_expr("g", srcs).c_str()));
     }
+  } else if (m.family == Module::kBg) {
+    for (int j = 0; j < W; j++) out.push_back(fmt("  c[%d] = %s;", j, bg_row_pair_expr(m, lay.ra[j], lay.rb[j]).c_str()));
   } else {
     for (int h = 0; h < (NCH() + 3) / 4; h++)
       for (int k = 0; k < 16; k++) {
@@ -477,6 +496,63 @@ void emit_score_cm(const Module& m, Lines& out) {
       out.push_back(fmt("  if ((%s) != 0u) return %du;", exprs[0].second.c_str(), exprs[0].first));
   }
   out.push_back(fmt("  return %du;", nrows));
+  out.push_back("}");
+}
+
+// ---- bit-gather family: arbitrary scan tables ------------------------------------------------------------------------------
+// source bits of scan row j grouped by source word: word -> mask (for the zero test of the scoring pass)
+std::map<int, uint32_t> bg_row_masks(const Module& m, int j) {
+  std::map<int, uint32_t> by_word;
+  for (int q = 0; q < 16; q++) {
+    const size_t i = (size_t)16 * j + q;
+    if (i < m.bits.size()) by_word[m.bits[i] / 32] |= 1u << (m.bits[i] % 32);
+  }
+  return by_word;
+}
+
+// expression for the encoder word holding rows ra (low halfword) and rb (high halfword), scan position 0 in bit 15 of a halfword
+std::string bg_row_pair_expr(const Module& m, int ra, int rb) {
+  std::map<std::pair<int, int>, uint32_t> groups;  // (source word, right-shift distance) -> mask of target bits
+  for (int half = 0; half < 2; half++) {
+    const int row = half ? rb : ra;
+    for (int q = 0; q < 16; q++) {
+      const size_t i = (size_t)16 * row + q;
+      if (i >= m.bits.size()) continue;
+      const int t = 16 * half + 15 - q, b = m.bits[i] % 32;
+      groups[{m.bits[i] / 32, b - t}] |= 1u << t;
+    }
+  }
+  if (groups.empty()) return "0u";
+  std::vector<std::string> terms;
+  for (auto& kv : groups) {
+    const int w = kv.first.first, sh = kv.first.second;
+    if (sh == 0) terms.push_back(fmt("(g[%d] & 0x%08xu)", w, kv.second));
+    else if (sh > 0) terms.push_back(fmt("((g[%d] >> %d) & 0x%08xu)", w, sh, kv.second));
+    else terms.push_back(fmt("((g[%d] << %d) & 0x%08xu)", w, -sh, kv.second));
+  }
+  return join(terms, " | ");
+}
+
+// Leading zero rows of a bit-gather module: the XOR-ed residue words a row reads are computed when first needed, a row is zero
+// iff its source bits are (one AND-OR per source word), and the walk stops at the first non-zero row (VPC.cpp:378-387).
+void emit_score_bg(const Module& m, Lines& out) {
+  out.push_back(fmt("__device__ __forceinline__ uint32_t score_%d(const uint32_t (&x)[32]) {", m.idx));
+  out.push_back("  uint32_t g[32];");
+  std::set<int> have;
+  for (int j = 0; j < R(); j++) {
+    const auto masks = bg_row_masks(m, j);
+    if (masks.empty()) continue;  // past the end of a short table: always zero
+    std::vector<std::string> terms;
+    for (auto& wm : masks) {
+      if (!have.count(wm.first)) {
+        out.push_back("  { " + m.residue_stmts(wm.first, "r") + fmt(" g[%d] = %s; }", wm.first, m.g_from_r(wm.first, "r").c_str()));
+        have.insert(wm.first);
+      }
+      terms.push_back(wm.second == 0xFFFFFFFFu ? fmt("g[%d]", wm.first) : fmt("(g[%d] & 0x%08xu)", wm.first, wm.second));
+    }
+    out.push_back(fmt("  if ((%s) != 0u) return %du;", join(terms, " | ").c_str(), j));
+  }
+  out.push_back(fmt("  return %du;", R()));
   out.push_back("}");
 }
 
@@ -769,20 +845,23 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
     const char* e2 = getenv("MPC_SPEC_PM2");
     if (e2 && e2[0] == '0') t.pm2 = false;
   }
+  bool has_bg = false;
   for (auto& m : mods) {
     if (m.family == Module::kPm) has_pm = true;
     else { has_cm = true; all_c = all_c && m.cxor; any_c = any_c || m.cxor; }
+    if (m.family == Module::kBg) has_bg = true;
   }
   const char* e;
   t.eligible = true;
   t.line_size = cfg.line_size;
   t.use_lut = has_cm && !((e = getenv("MPC_SPEC_LUT")) && e[0] == '0');
   t.lut_xor = 0;
-  if (t.use_lut && !((e = getenv("MPC_SPEC_LUTXOR")) && e[0] == '0')) t.lut_xor = all_c ? 1 : (!any_c ? 2 : 0);
+  // (bit-gather rows take single bits of the XOR-ed residues: the stage cannot be folded into the table)
+  if (t.use_lut && !has_bg && !((e = getenv("MPC_SPEC_LUTXOR")) && e[0] == '0')) t.lut_xor = all_c ? 1 : (!any_c ? 2 : 0);
   // column-major only: ONE CTA of 20 warps per SM at 96 registers (the next allocation step down, 80, spills), one
   // 4 KiB tile stage per warp; measured on B200: 16 warps x 2 stages 4.11 TB/s, 18 x 1 4.16, 20 x 1 4.26, 21/22/24 x 1 (80
   // registers) 3.86-3.93 on the headline workload
-  t.warps = (t.use_lut && !has_pm) ? 20 : 16;
+  t.warps = (t.use_lut && !has_pm && !has_bg) ? 20 : 16;
   // configs with plane-major modules: ONE CTA of 16 warps at 128 registers (measured against 8 warps at 160 registers, the
   // former choice: P6 smooth 1.42 -> 1.79 TB/s, random 2.23 -> 2.72, E5 mixed 2.08 -> 2.82; 20 warps at 96 registers spill)
   t.stages = 1;
@@ -828,7 +907,7 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
     // Column-major configs get BOTH forms: a warp whose stage-3 lanes all picked the same module (homogeneous data -- the
     // common case) runs that module's fused pass, any other warp the per-module residue passes followed by the ONE shared
     // classifier (measured: fused +1.5 % on smooth / random data, shared +25 % on finely mixed data; MPC_SPEC_ADAPTIVE=0/1).
-    t.adaptive_encode = !t.fused_encode && !has_pm && t.use_lut;
+    t.adaptive_encode = !t.fused_encode && !has_pm && !has_bg && t.use_lut;
     if ((e = getenv("MPC_SPEC_ADAPTIVE"))) t.adaptive_encode = e[0] == '1' && !t.fused_encode;
   }
   return t;
@@ -862,18 +941,21 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   RowLayout lay;
   {
     std::vector<std::vector<int>> cm_cols;
-    for (auto& m : mods)
+    bool any_bg = false;
+    for (auto& m : mods) {
       if (m.family == Module::kCm) { cm_cols.push_back(m.cols); cm_cols.back().resize(L, -1); }
-    lay = plan_row_layout(t.use_lut ? cm_cols : std::vector<std::vector<int>>());
+      any_bg = any_bg || m.family == Module::kBg;
+    }
+    lay = plan_row_layout((t.use_lut && !any_bg) ? cm_cols : std::vector<std::vector<int>>());
   }
   if (lay.paired) emit_encode_rows(lay, out);
   for (auto& m : mods) {
     out.push_back(fmt("// ---- module %d: %s, root %d, %s XOR, %s-major scan ----", m.idx, kPredNames[m.predictor], m.root,
-                      m.cxor ? "consecutive" : "first-plane", m.family == Module::kCm ? "column" : "plane"));
+                      m.cxor ? "consecutive" : "first-plane", m.family == Module::kCm ? "column" : (m.family == Module::kPm ? "plane" : "bit-gather (arbitrary table), row")));
     if (t.pm2) {
       emit_res_pm2(m, out);
     } else {
-      if (m.family == Module::kCm) emit_score_cm(m, out); else emit_score_pm(m, out);
+      if (m.family == Module::kCm) emit_score_cm(m, out); else if (m.family == Module::kPm) emit_score_pm(m, out); else emit_score_bg(m, out);
       emit_full(m, out, t.lut_xor, lay);
     }
     out.push_back("");
@@ -934,7 +1016,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   // encoder families in use: column-major, or plane-major with a given pair of plane selectors
   std::vector<std::pair<int, std::pair<unsigned, unsigned>>> fams;
   auto fam_of = [&](const Module& m) {
-    return std::make_pair(m.family == Module::kCm ? 0 : 1, m.family == Module::kPm ? pm_selectors(m) : std::make_pair(0u, 0u));
+    return std::make_pair(m.family == Module::kPm ? 1 : 0, m.family == Module::kPm ? pm_selectors(m) : std::make_pair(0u, 0u));
   };
   for (auto& m : mods)
     if (std::find(fams.begin(), fams.end(), fam_of(m)) == fams.end()) fams.push_back(fam_of(m));

@@ -216,9 +216,10 @@ def test_shipped_configs_use_the_specialised_kernel(mpcb, cfg):
     assert m.kernel_name() == "spec_thread:" + cfg
 
 
-def test_ineligible_config_falls_back_to_generic_and_says_so(mpcb):
+def test_ineligible_config_falls_back_to_generic_and_says_so(mpcb, monkeypatch):
     rng = np.random.default_rng(5)
-    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(random_config(rng, L=64, n_pred=2))))
+    monkeypatch.setenv("MPC_SPEC_BITGATHER", "0")  # arbitrary scan tables left to the generic kernel
+    m = mpcb.Mpc(mpcb.load_config(text=json.dumps(random_config(rng, L=64, n_pred=2, table="perm"))))
     assert m.kernel_name() == "generic_warp"
     with pytest.raises(mpcb.MpcError) as e:
         m.set_kernel(2)

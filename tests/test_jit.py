@@ -38,11 +38,22 @@ def test_random_eligible_configs_compile(mpcb, seed):
     assert rc == 0 and nbytes > 10000, log
 
 
-def test_ineligible_configs_are_reported(mpcb):
+def test_ineligible_configs_are_reported(mpcb, monkeypatch):
     rng = np.random.default_rng(1)
+    monkeypatch.setenv("MPC_SPEC_BITGATHER", "0")  # arbitrary scan tables left to the generic kernel
     pod = mpcb.load_config(text=json.dumps(random_config(rng, L=128, n_pred=2, table="perm")))
     rc, _, log = mpcb.jit_compile_check(pod)
     assert rc == -2 and "neither column-major nor plane-major" in log
+
+
+@pytest.mark.parametrize("L", [32, 128])
+@pytest.mark.parametrize("table", ["perm", "dup", "short"])
+def test_arbitrary_scan_tables_compile(mpcb, table, L):
+    """any (row, column) table (ScanModule.cpp:6-22) -- permutations, duplicates, short tables: the bit-gather family"""
+    rng = np.random.default_rng(L + len(table))
+    pod = mpcb.load_config(text=json.dumps(random_config(rng, L=L, n_pred=2, table=table)))
+    rc, nbytes, log = mpcb.jit_compile_check(pod)
+    assert rc == 0 and nbytes > 5000, log
 
 
 def shared_scan_pm_config(seed, L):
@@ -93,6 +104,17 @@ def check_jit_config(mpcb, cfg, seed, L=128, n=3000):
 def test_short_line_jit_kernels_match_oracle(mpcb, seed, L):
     """32- and 64-byte lines on the thread-per-block kernel: four / two lines per thread; ragged count on purpose"""
     check_jit_config(mpcb, eligible_config(200 + seed, L), seed, L, n=3001 + seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [32, 64, 128])
+@pytest.mark.parametrize("table", ["perm", "dup", "short", "random"])
+@pytest.mark.parametrize("seed", range(2))
+def test_arbitrary_scan_table_jit_kernels_match_oracle(mpcb, seed, table, L):
+    """arbitrary scan tables on the thread-per-block kernel (bit-gather family), also mixed with the other families"""
+    rng = np.random.default_rng(1000 * L + 10 * seed + len(table))
+    cfg = random_config(rng, L=L, n_pred=int(rng.integers(1, 4)), table=table)
+    check_jit_config(mpcb, cfg, seed, L, n=2000 + seed)
 
 
 @pytest.mark.gpu
