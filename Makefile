@@ -23,7 +23,7 @@ tools/int_peak: tools/int_peak.cu
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 
 # config compiler (csrc/mpc_specgen.cpp): one specialised schedule per shipped config; generated sources are committed
-tools/specgen: tools/specgen_main.cpp $(CSRC)/mpc_specgen.cpp $(CSRC)/mpc_specgen.h $(CSRC)/mpc_config.cpp include/mpc_capi.h
+tools/specgen: tools/specgen_main.cpp $(CSRC)/mpc_specgen.cpp $(CSRC)/mpc_specgen.h $(CSRC)/mpc_layout.h $(CSRC)/mpc_config.cpp include/mpc_capi.h
 	$(CXX) -O1 -std=c++17 -Iinclude -I$(CSRC) tools/specgen_main.cpp $(CSRC)/mpc_specgen.cpp $(CSRC)/mpc_config.cpp -o $@
 $(CSRC)/spec/.stamp: tools/specgen $(foreach c,$(SPEC_CFGS),configs/$(c).json)
 	@mkdir -p $(CSRC)/spec

@@ -342,7 +342,7 @@ int mpc_create(const mpc_config_pod* cfg, int device, mpc_ctx** out) {
     }
   }
   {
-    std::vector<uint8_t> lut(65536);
+    std::vector<uint8_t> lut(mpc::kRowLutBytes);
     mpc::build_row_cost_lut(lut.data(), ctx->spec ? ctx->spec->lut_xor : (ctx->jit ? mpc::jit_lut_xor(ctx->jit) : 0));
     MPC_CREATE_CUDA(cudaMalloc(&ctx->d_row_lut, lut.size()));
     MPC_CREATE_CUDA(cudaMemcpy(ctx->d_row_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));

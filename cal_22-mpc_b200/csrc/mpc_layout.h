@@ -11,6 +11,12 @@ constexpr unsigned long long kStatsWords = 2ull * kK + (unsigned long long)kK * 
 constexpr unsigned long long kResAbsOff = 0;
 constexpr unsigned long long kResSqOff = kK;
 constexpr unsigned long long kHistOff = 2 * kK;
+// Row-cost table of the specialised kernels (column-major scans): entry of the 16-bit scan row (A << 8) | B sits at byte
+// 260 * A + B.  The skew of 4 bytes per value of A spreads rows whose low byte is zero (common: the more significant byte of a
+// small delta) over the shared-memory banks -- with the plain index A * 256 + B they all fall into bank 0 -- and costs nothing:
+// the kernels form both indices of a word of two rows with one IDP.2A each (dot products with (260, 1)).
+constexpr unsigned kRowLutSkew = 260;
+constexpr unsigned kRowLutBytes = 66560;  // >= 260 * 255 + 255 + 1, a multiple of 16
 // A CUtensorMap (128 bytes, 64-byte aligned) as the kernels see it: opaque, so that the NVRTC build needs no cuda.h.
 // Describes the dump as a [n_blocks][128 B] uint8 tensor with a 32 x 128 B box and the 128-byte swizzle
 // (make_tile_tmap, mpc_jit.cpp).

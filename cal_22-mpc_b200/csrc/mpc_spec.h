@@ -16,7 +16,8 @@ struct SpecKernel {
   int lut_xor;  // which row-cost table the kernel expects (0 plain, 1 consecutive-XOR folded in, 2 first-plane-XOR folded in)
 };
 
-// 65 536-entry table of the common encoder's cost of a non-zero 16-bit scan row (0 for the zero row), FPCModule.cpp:47-66
+// table of the common encoder's cost of a non-zero 16-bit scan row (0 for the zero row), FPCModule.cpp:47-66, in the skewed
+// layout of mpc_layout.h (kRowLutBytes bytes)
 void build_row_cost_lut(uint8_t* lut, int lut_xor);
 
 // true when the two configs describe the same computation (fields the kernels depend on)

@@ -3,6 +3,7 @@
 
 #include "mpc_spec.h"
 #include "mpc_device.cuh"
+#include "mpc_layout.h"
 
 namespace mpc {
 
@@ -37,12 +38,13 @@ bool spec_pod_equal(const mpc_config_pod& a, const mpc_config_pod& b) {
 }
 
 void build_row_cost_lut(uint8_t* lut, int lut_xor) {
+  memset(lut, 0, kRowLutBytes);
   for (uint32_t v = 0; v < 65536; v++) {
     uint32_t row = v;  // two residue bytes; with lut_xor the XOR stage (XORModule.cpp:9-20) is applied here, per byte
     if (lut_xor == 1) row = mpcdev::xor_planes_consecutive(v, 0) & 0xffffu;
     else if (lut_xor == 2) row = mpcdev::xor_planes_first(v, 0) & 0xffffu;
     uint32_t nz;
-    lut[v] = (uint8_t)(mpcdev::row2_cost(row, &nz) & 0xffu);
+    lut[kRowLutSkew * (v >> 8) + (v & 0xffu)] = (uint8_t)(mpcdev::row2_cost(row, &nz) & 0xffu);  // skewed layout, mpc_layout.h
   }
 }
 

@@ -14,6 +14,7 @@
 // Eligible: lineSize 32 / 64 / 128 and every PredComp scan table column-major or plane-major; everything else stays on the
 // generic warp-per-block kernel.
 #include "mpc_specgen.h"
+#include "mpc_layout.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -877,7 +878,7 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   // of the stage before the next copy), so cp.async stays the default.
   t.tma = t.stages == 1 && cfg.line_size == 128 && (e = getenv("MPC_SPEC_TMA")) && e[0] == '1';
   t.smem_bytes = (size_t)t.warps * t.stages * 4096 + (t.tma ? (size_t)((t.warps * 8 + 15) / 16) * 16 : 0) + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
-                 (t.use_lut ? 65536 : 0);
+                 (t.use_lut ? (size_t)kRowLutBytes : 0);
   // Regrouping queues (mpc_spec.cuh): one queue per PredComp module in the shared memory that is left (227 KiB per CTA on sm_100,
   // 1 KiB of it reserved by the driver); an entry is the block (128 B) + its index + a flag word.  At least two batches of 32 per
   // queue, else the kernel runs without them (MPC_SPEC_REGROUP=0 switches them off for A/B runs).
