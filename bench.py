@@ -350,8 +350,11 @@ def int_roofline(job, kernel_name, n_blocks, kernel_ms):
         t_alu = warp_inst.get("alu", 0) / (peaks["lop3"]["warp_inst_per_clk_per_sm"] * sms * clk)
         t_fma = warp_inst.get("fma", 0) / (peaks["imad"]["warp_inst_per_clk_per_sm"] * sms * clk)
         t_issue = warp_inst.get("total", 0) / (4.0 * sms * clk)  # one warp instruction per clock per scheduler
-        t_int = max(t_alu, t_fma, t_issue)
-        return {"ops_per_block": ipb, "source": prof.get("inst_source"),
+        # shared-memory data pipe: one 128-byte wavefront per clock per SM (row-cost lookups with their bank conflicts + tile staging)
+        t_smem = prof.get("smem_wavefronts_per_block", 0) * n_blocks / 32.0 / (sms * clk)
+        t_int = max(t_alu, t_fma, t_issue, t_smem)
+        return {"ops_per_block": ipb, "smem_wavefronts_per_block": prof.get("smem_wavefronts_per_block"), "t_smem_ms": 1e3 * t_smem,
+                "source": prof.get("inst_source"),
                 "peak_measured": {k: peaks[k]["warp_inst_per_clk_per_sm"] for k in ("lop3", "iadd3", "imad", "prmt", "shf", "vimnmx_u16x2", "idp4a", "mix_lop3_imad")},
                 "peak_unit": "warp instructions per clock per SM (tools/int_peak, this run)",
                 "t_alu_ms": 1e3 * t_alu, "t_fma_ms": 1e3 * t_fma, "t_issue_ms": 1e3 * t_issue, "t_int_ms": 1e3 * t_int,
