@@ -42,6 +42,8 @@ int pfail(int code, const std::string& what) { g_perr = what; return code; }
     if (e__ != cudaSuccess) return pfail(MPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
+// W = words per line: a thread holds 128 bytes = 32 / W consecutive lines (the analysis takes any line size, Pattern.cpp:6-75)
+template <int W>
 __global__ void __launch_bounds__(kThreads)
 pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __restrict__ sizes, uint64_t* __restrict__ hashes,
                unsigned long long* __restrict__ stats) {
@@ -53,26 +55,34 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
   for (int i = threadIdx.x; i < 512; i += kThreads) s_hist[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  tile::for_each_block(lines, n_blocks, s_stage + warp * tile::kStages * 256, kWarps,
-                       [&](const uint32_t (&x)[32], uint64_t blk, bool valid) {
+  constexpr int S = 32 / W;
+  tile::for_each_block(lines, (n_blocks + S - 1) / S, s_stage + warp * tile::kStages * 256, kWarps,
+                       [&](const uint32_t (&x128)[32], uint64_t unit, bool) {
+#pragma unroll
+   for (int sub = 0; sub < S; sub++) {
+    uint32_t x[32];
+#pragma unroll
+    for (int i = 0; i < W; i++) x[i] = x128[sub * W + i];
+    const uint64_t blk = unit * S + sub;
+    const bool valid = blk < n_blocks;
     uint32_t any = 0, rep = 0;
 #pragma unroll
-    for (int i = 0; i < 32; i++) { any |= x[i]; rep |= x[i] ^ x[0]; }
+    for (int i = 0; i < W; i++) { any |= x[i]; rep |= x[i] ^ x[0]; }
     const bool is_zero = valid && any == 0;   // Pattern::isZeros
     const bool is_rep = valid && rep == 0;    // Pattern::isRepeated(line, 4) == PatternResult::IsAllWordSame
     int sel;
     uint32_t imm;
     struct { __device__ __forceinline__ bool operator()(bool b) const { return __all_sync(0xffffffffu, b) != 0; } } vote;  // every lane is here
-    const uint32_t size = mpcvar::pattern_block<32>(x, &sel, &imm, vote);
+    const uint32_t size = mpcvar::pattern_block<W>(x, &sel, &imm, vote);
     if (valid && sizes) sizes[blk] = (uint16_t)size;
-    if (valid && hashes) hashes[blk] = mpcvar::block_hash64(x);
-    // byte histograms (PatternResult::UpdateCountMap): a word-repeating line is 32 copies of its first word
+    if (valid && hashes) hashes[blk] = mpcvar::block_hash64<W>(x);
+    // byte histograms (PatternResult::UpdateCountMap): a word-repeating line is W copies of its first word
     if (is_rep) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) atomicAdd(&s_hist[(x[0] >> (8 * k)) & 0xffu], 32u);
+      for (int k = 0; k < 4; k++) atomicAdd(&s_hist[(x[0] >> (8 * k)) & 0xffu], (uint32_t)W);
     } else if (valid) {
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
+      for (int i = 0; i < W; i++) {
 #pragma unroll
         for (int k = 0; k < 4; k++) atomicAdd(&s_hist[256 + ((x[i] >> (8 * k)) & 0xffu)], 1u);
       }
@@ -94,7 +104,8 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
         if (lane == 0) { atomicAdd(&s_cnt[3 + p], (unsigned long long)c); atomicAdd(&s_cnt[9 + p], (unsigned long long)s); }
       }
     }
-  });
+   }  // sub-lines
+  }, n_blocks * (uint64_t)(W / 4));
   __syncthreads();
   if (threadIdx.x < kCnt && s_cnt[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_cnt[threadIdx.x]);
   for (int i = threadIdx.x; i < 512; i += kThreads)
@@ -109,15 +120,14 @@ __global__ void iota_kernel(uint32_t* __restrict__ v, uint32_t n) {
 // sorted (hash, index) pairs: a line whose hash equals its predecessor's is a duplicate when the 128 bytes agree, and
 // a hash collision otherwise (the caller then falls back to the exact host pass)
 __global__ void dup_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, const uint4* __restrict__ lines,
-                           uint32_t n, unsigned long long* __restrict__ stats) {
+                           uint32_t n, uint32_t chunks, unsigned long long* __restrict__ stats) {  // chunks = line size / 16
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   bool dup = false, coll = false;
   if (j >= 1 && j < n && keys[j] == keys[j - 1]) {
-    const uint4* a = lines + (uint64_t)idx[j] * 8;
-    const uint4* b = lines + (uint64_t)idx[j - 1] * 8;
+    const uint4* a = lines + (uint64_t)idx[j] * chunks;
+    const uint4* b = lines + (uint64_t)idx[j - 1] * chunks;
     uint32_t d = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (uint32_t k = 0; k < chunks; k++) {
       const uint4 p = a[k], q = b[k];
       d |= (p.x ^ q.x) | (p.y ^ q.y) | (p.z ^ q.z) | (p.w ^ q.w);
     }
@@ -207,7 +217,7 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
                        uint64_t cache_blocks, uint16_t* d_sizes, mpc_pattern_stats* out, float* kernel_ms) {
   using namespace mpc;
   if (!out || (n_blocks && !d_lines)) return pfail(MPC_E_ARG, "null argument");
-  if (line_size != 128) return pfail(MPC_E_ARG, "the GPU pattern analysis is built for 128-byte blocks");
+  if (line_size != 32 && line_size != 64 && line_size != 128) return pfail(MPC_E_ARG, "line size must be 32, 64 or 128 bytes");
   if ((uintptr_t)d_lines & 15) return pfail(MPC_E_ARG, "lines must be 16-byte aligned");
   if (n_blocks >= (1ull << 31)) return pfail(MPC_E_ARG, "too many blocks for 32-bit line indices");
   if (cache_blocks == 0) cache_blocks = (1ull << 24) - 1;  // CACHESIZE, LRU.h:6
@@ -223,17 +233,25 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
   cudaEventRecord(ev.a, 0);
   if (n) {
     const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
-    PAT_CUDA(cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    PAT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pattern_kernel, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const uint64_t tiles = (n_blocks + tile::kTileBlocks - 1) / tile::kTileBlocks;
-    uint64_t grid = (uint64_t)sms * per_sm;
-    const uint64_t want = (tiles + kWarps - 1) / kWarps;
-    if (grid > want) grid = want;
-    pattern_kernel<<<(unsigned)grid, kThreads, smem>>>(reinterpret_cast<const uint4*>(d_lines), n_blocks, d_sizes,
-                                                       (uint64_t*)keys.p, (unsigned long long*)stats.p);
-    PAT_CUDA(cudaGetLastError());
+    auto launch = [&](auto kernel, uint64_t lines_per_unit) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+      if (e != cudaSuccess) return e;
+      if (per_sm < 1) per_sm = 1;
+      const uint64_t units = (n_blocks + lines_per_unit - 1) / lines_per_unit;  // 128-byte units
+      const uint64_t tiles = (units + tile::kTileBlocks - 1) / tile::kTileBlocks;
+      uint64_t grid = (uint64_t)sms * per_sm;
+      const uint64_t want = (tiles + kWarps - 1) / kWarps;
+      if (grid > want) grid = want;
+      kernel<<<(unsigned)grid, kThreads, smem>>>(reinterpret_cast<const uint4*>(d_lines), n_blocks, d_sizes, (uint64_t*)keys.p,
+                                                 (unsigned long long*)stats.p);
+      return cudaGetLastError();
+    };
+    if (line_size == 32) PAT_CUDA(launch(pattern_kernel<8>, 4));
+    else if (line_size == 64) PAT_CUDA(launch(pattern_kernel<16>, 2));
+    else PAT_CUDA(launch(pattern_kernel<32>, 1));
     // temporal locality: sort (hash, index), confirm equal-hash neighbours on the bytes
     PAT_CUDA(cudaMalloc(&keys2.p, (size_t)n * 8));
     PAT_CUDA(cudaMalloc(&idx.p, (size_t)n * 4));
@@ -246,7 +264,7 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
     PAT_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, (const uint64_t*)keys.p, (uint64_t*)keys2.p, (const uint32_t*)idx.p,
                                              (uint32_t*)idx2.p, (int)n));
     dup_kernel<<<(n + 255) / 256, 256>>>((const uint64_t*)keys2.p, (const uint32_t*)idx2.p, reinterpret_cast<const uint4*>(d_lines), n,
-                                         (unsigned long long*)stats.p);
+                                         line_size / 16, (unsigned long long*)stats.p);
     PAT_CUDA(cudaGetLastError());
   }
   cudaEventRecord(ev.b, 0);

@@ -47,6 +47,8 @@ __global__ void pack_count_symbol(const uint32_t* __restrict__ sym, const uint32
 constexpr int kHashSlots = 4096;
 __host__ __device__ __forceinline__ uint32_t sc2_hash(uint32_t v) { return (v * 0x9E3779B1u) >> 20; }
 
+// W = words per line: a thread holds 128 bytes = 32 / W consecutive lines (SC2 works word by word, SC2.cpp:315-330, so any line size)
+template <int W>
 __global__ void __launch_bounds__(kThreads)
 sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t first_block, uint64_t sampling, const uint32_t* __restrict__ g_keys,
                   const uint8_t* __restrict__ g_lens, uint16_t* __restrict__ sizes, unsigned long long* __restrict__ total) {
@@ -57,17 +59,25 @@ sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t f
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long bits = 0;
-  tile::for_each_block(lines, n_blocks, s_stage + warp * tile::kStages * 256, kWarps,
-                       [&](const uint32_t (&x)[32], uint64_t blk, bool valid) {
+  constexpr int S = 32 / W;
+  tile::for_each_block(lines, (n_blocks + S - 1) / S, s_stage + warp * tile::kStages * 256, kWarps,
+                       [&](const uint32_t (&x128)[32], uint64_t unit, bool) {
+#pragma unroll
+   for (int sub = 0; sub < S; sub++) {
+    uint32_t x[32];
+#pragma unroll
+    for (int i = 0; i < W; i++) x[i] = x128[sub * W + i];
+    const uint64_t blk = unit * S + sub;
+    const bool valid = blk < n_blocks;
     uint32_t size = 0;
     if (first_block + blk < sampling) {
-      size = 33u * 32u;  // sampling phase: every word is a miss (SC2.cpp:315-323 with an empty code map)
+      size = 33u * (uint32_t)W;  // sampling phase: every word is a miss (SC2.cpp:315-323 with an empty code map)
     } else {
       // first probe of all 32 words with no branch in between (32 independent loads in flight); only a word whose first slot
       // holds another symbol walks on
       uint32_t pending = 0;  // bit j: word j has to look at further slots
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
+      for (int j = 0; j < W; j++) {
         const uint2 e = s_tab[sc2_hash(x[j])];
         const bool hit = e.y != 0u && e.x == x[j];
         size += hit ? e.y - 1u : 33u;
@@ -75,7 +85,7 @@ sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t f
       }
       if (pending) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
+        for (int j = 0; j < W; j++) {
           if ((pending >> j) & 1u) {
             const uint32_t v = x[j];
             uint32_t idx = (sc2_hash(v) + 1u) & (kHashSlots - 1);
@@ -93,7 +103,8 @@ sc2_lookup_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint64_t f
       if (sizes) sizes[blk] = (uint16_t)size;
       bits += size;
     }
-  });
+   }  // sub-lines
+  }, n_blocks * (uint64_t)(W / 4));
   for (int o = 16; o; o >>= 1) bits += __shfl_down_sync(0xffffffffu, bits, o);
   if (lane == 0 && bits) atomicAdd(total, bits);
 }
@@ -226,10 +237,10 @@ int ws_reserve(Sc2Workspace& w, size_t words) {
 extern "C" int mpc_sc2_build_table(int device, const uint8_t* d_lines, uint64_t sampling_lines, uint32_t line_size, mpc_sc2_table* table) {
   using namespace mpc;
   if (!table || (sampling_lines && !d_lines)) return fail(MPC_E_ARG, "null argument");
-  if (line_size != 128) return fail(MPC_E_ARG, "the GPU variants are built for 128-byte blocks");
+  if (line_size != 32 && line_size != 64 && line_size != 128) return fail(MPC_E_ARG, "line size must be 32, 64 or 128 bytes");
   memset(table, 0, sizeof(*table));
   if (sampling_lines == 0) return MPC_OK;
-  const uint64_t nw64 = sampling_lines * 32ull;
+  const uint64_t nw64 = sampling_lines * (uint64_t)(line_size / 4);
   if (nw64 > 0x7fffffffull) return fail(MPC_E_ARG, "sampling window too large");
   const int nw = (int)nw64;
   std::lock_guard<std::mutex> lock(g_ws_mutex);
@@ -277,7 +288,7 @@ extern "C" int mpc_sc2_apply_device(int device, const uint8_t* d_lines, uint64_t
                                     uint32_t line_size, const mpc_sc2_table* table, uint16_t* d_sizes, mpc_variant_stats* out, float* kernel_ms) {
   using namespace mpc;
   if (!out || !table || (n_blocks && !d_lines)) return fail(MPC_E_ARG, "null argument");
-  if (line_size != 128) return fail(MPC_E_ARG, "the GPU variants are built for 128-byte blocks");
+  if (line_size != 32 && line_size != 64 && line_size != 128) return fail(MPC_E_ARG, "line size must be 32, 64 or 128 bytes");
   if ((uintptr_t)d_lines & 15) return fail(MPC_E_ARG, "lines must be 16-byte aligned");
   if (table->n > 1024) return fail(MPC_E_ARG, "code table holds more than 1024 symbols");
   std::lock_guard<std::mutex> lock(g_ws_mutex);
@@ -302,15 +313,23 @@ extern "C" int mpc_sc2_apply_device(int device, const uint8_t* d_lines, uint64_t
   SC2_CUDA(cudaMemsetAsync(w.d_total, 0, 8, 0));
   if (n_blocks) {
     const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
-    SC2_CUDA(cudaFuncSetAttribute(sc2_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    SC2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc2_lookup_kernel, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const uint64_t tiles = (n_blocks + 31) / 32;
-    const uint64_t grid = std::min<uint64_t>((uint64_t)sms * per_sm, (tiles + kWarps - 1) / kWarps);
-    sc2_lookup_kernel<<<(unsigned)grid, kThreads, smem>>>(reinterpret_cast<const uint4*>(d_lines), n_blocks, first_block, sampling_lines,
-                                                          w.d_tab_keys, w.d_tab_lens, d_sizes, w.d_total);
-    SC2_CUDA(cudaGetLastError());
+    auto launch = [&](auto kernel, uint64_t lines_per_unit) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      int per_sm = 1;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+      if (e != cudaSuccess) return e;
+      if (per_sm < 1) per_sm = 1;
+      const uint64_t units = (n_blocks + lines_per_unit - 1) / lines_per_unit;  // 128-byte units
+      const uint64_t tiles = (units + 31) / 32;
+      const uint64_t grid = std::min<uint64_t>((uint64_t)sms * per_sm, (tiles + kWarps - 1) / kWarps);
+      kernel<<<(unsigned)grid, kThreads, smem>>>(reinterpret_cast<const uint4*>(d_lines), n_blocks, first_block, sampling_lines,
+                                                 w.d_tab_keys, w.d_tab_lens, d_sizes, w.d_total);
+      return cudaGetLastError();
+    };
+    if (line_size == 32) SC2_CUDA(launch(sc2_lookup_kernel<8>, 4));
+    else if (line_size == 64) SC2_CUDA(launch(sc2_lookup_kernel<16>, 2));
+    else SC2_CUDA(launch(sc2_lookup_kernel<32>, 1));
   }
   SC2_CUDA(cudaEventRecord(w.e1, 0));
   unsigned long long total = 0;
@@ -358,7 +377,7 @@ extern "C" int mpc_sc2_run_host(int device, const uint8_t* h_lines, uint64_t n_b
                                 uint16_t* h_sizes, mpc_variant_stats* out, float* kernel_ms) {
   using namespace mpc;
   if (!out || (n_blocks && !h_lines)) return fail(MPC_E_ARG, "null argument");
-  if (line_size != 128) return fail(MPC_E_ARG, "the GPU variants are built for 128-byte blocks");
+  if (line_size != 32 && line_size != 64 && line_size != 128) return fail(MPC_E_ARG, "line size must be 32, 64 or 128 bytes");
   SC2_CUDA(cudaSetDevice(device));
   const uint64_t chunk = (256ull << 20) / line_size;
   const bool build = n_blocks > sampling_lines && sampling_lines > 0;

@@ -294,10 +294,11 @@ MPC_HD uint32_t pattern_block(const uint32_t (&x)[32], int* sel_out, uint32_t* i
 
 // 64-bit content hash of a block (temporal-locality pass: equal blocks are found by sorting the hashes, and every
 // match is confirmed on the 128 bytes themselves, so the hash only has to spread well)
+template <int W = 32>
 MPC_HD uint64_t block_hash64(const uint32_t (&x)[32]) {
   uint64_t h = 0x9E3779B97F4A7C15ull;
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
+  for (int i = 0; i < W / 2; i++) {
     const uint64_t v = (uint64_t)x[2 * i] | ((uint64_t)x[2 * i + 1] << 32);
     h = (h ^ v) * 0xFF51AFD7ED558CCDull;
     h ^= h >> 29;

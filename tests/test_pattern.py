@@ -118,6 +118,21 @@ def check_against_oracle(mpcb, d, cache_blocks=0):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("L", [32, 64])
+def test_gpu_short_lines(mpcb, L):
+    """32- / 64-byte lines: four / two lines per thread, duplicates confirmed on L bytes; ragged counts, a cache that evicts"""
+    rng = np.random.default_rng(L)
+    for d, cache in ((np.concatenate([dump_with_repeats().reshape(-1, L), random_blocks(rng, 1501, L)]), 0),
+                     (synth("mixed_hashed", 5, 0, 900, 900).reshape(-1, L)[:-3], 0),
+                     (np.concatenate([random_blocks(rng, 300, L)] * 3), 100)):
+        sizes, st, _ = mpcb.pattern_run(d, cache_blocks=cache, line_size=L)
+        want, words = oracle_pattern(d, L, cache or (1 << 24) - 1)
+        assert np.array_equal(sizes.astype(np.uint32), want)
+        assert np.array_equal(st.words(), words)
+        assert st.blocks == d.shape[0]
+
+
+@pytest.mark.gpu
 def test_gpu_known_answers_and_classes(mpcb):
     sizes, st, _ = mpcb.pattern_run(kat_blocks())
     assert sizes.tolist() == KAT

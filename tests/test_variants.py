@@ -135,6 +135,10 @@ def test_cpack_sc2_oracles_match_reference():
     few = synth("sparse_i32", 3, 0, 40000, 40000)  # fewer than 1024 distinct symbols: no trimming
     rs, _ = RefCompressor("SC2", None, 128, 10000).compress(few)
     assert np.array_equal(oracle_sc2(few, 10000), rs)
+    for L in (32, 64):  # SC2 works word by word: the same dump bytes as shorter lines
+        dl = d.reshape(-1, L)[:50001]
+        rs, _ = RefCompressor("SC2", None, L, 12000).compress(dl)
+        assert np.array_equal(oracle_sc2(dl, 12000, L), rs), L
 
 
 def test_cpack_host_matches_oracle(mpcb):
@@ -159,6 +163,19 @@ def test_sc2_gpu_matches_oracle(mpcb, kind, n, S):
     assert bad.size == 0, (bad[:5], sizes[bad[:5]], want[bad[:5]])
     assert st.compressed_bits == int(want.astype(np.uint64).sum()) and st.original_bits == n * 1024
     assert mpcb.sc2_sampling_lines(n + 1) == max(10000, min((n + 1) // 100, 1000000))  # main.cpp:108-114
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [32, 64])
+def test_sc2_gpu_short_lines(mpcb, L):
+    from oracle.bridge import oracle_sc2
+    d = synth("mixed_hashed", 23, 0, 20000, 20000).reshape(-1, L)[:-3]  # ragged: the last 128-byte unit is partial
+    for S in (10000, 30000):
+        sizes, st, _ = mpcb.sc2_run(d, S, line_size=L)
+        want = oracle_sc2(d, S, L)
+        bad = np.nonzero(sizes.astype(np.uint32) != want)[0]
+        assert bad.size == 0, (L, S, bad[:5], sizes[bad[:5]], want[bad[:5]])
+        assert st.compressed_bits == int(want.astype(np.uint64).sum()) and st.original_bits == d.shape[0] * 8 * L
 
 
 @pytest.mark.gpu
