@@ -235,6 +235,20 @@ struct Module {
     return base;
   }
 
+  // Predicted word w as ONE byte gather over at most two line words, no arithmetic: *wa, *wb = source words, bytes[q] = (source
+  // word, byte) of lane q.  False for predictors that add or shift, or gather from three or four words.
+  bool pred_sel_form(int w, std::vector<int>* words, int (&src)[4]) const {
+    for (int q = 0; q < 4; q++) {
+      if (op == kShift && pval[4 * w + q] != 0) return false;
+      if (op == kAdd && (pval[4 * w + q] & 0xff) != 0) return false;
+      src[q] = psrc[4 * w + q];
+    }
+    words->clear();
+    for (int q = 0; q < 4; q++)
+      if (std::find(words->begin(), words->end(), src[q] / 4) == words->end()) words->push_back(src[q] / 4);
+    return words->size() <= 2;
+  }
+
   std::string root_byte() const {
     const int rw = root / 4, rb = root % 4;
     return rb == 0 ? fmt("(x[%d] & 0xffu)", rw) : fmt("((x[%d] >> %d) & 0xffu)", rw, 8 * rb);
@@ -249,9 +263,9 @@ struct Module {
   }
 
   // statement defining `const uint32_t <name>` = residue word w (before the XOR stage)
-  std::string residue_stmts(int w, const std::string& name, bool shared_low = false) const {
+  std::string residue_stmts(int w, const std::string& name, bool shared_low = false, const std::string& pred_override = std::string()) const {
     const int srcs[4] = {xsrc[4 * w], xsrc[4 * w + 1], xsrc[4 * w + 2], xsrc[4 * w + 3]};
-    const std::string xe = gather_expr("x", srcs), pe = pred_expr(w);
+    const std::string xe = gather_expr("x", srcs), pe = pred_override.empty() ? pred_expr(w) : pred_override;
     std::string e;
     int a = 0, b = 0;
     if (shared_low && plain_word(xe, &a) && plain_word(pe, &b))
@@ -380,7 +394,62 @@ std::string bg_row_pair_expr(const Module& m, int ra, int rb);
 // the stage is a per-byte bijection (Gray code / conditional complement), so it is folded into the table and disappears
 // from the kernel; only the root byte, which the XOR stage skips (XORModule.cpp:12), is run through the inverse map so
 // that the table maps it back to itself.
-void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay) {
+// ---- selector groups: ONE winner pass for several modules in warps whose lanes picked different winners -------------------
+// Modules whose predicted words are plain byte gathers over the SAME pair of line words differ only in the PRMT selector
+// (F4: "previous byte" = prmt(x[w-1], x[w], 0x6543) and "previous word" = x[w-1] = prmt(x[w-1], x[w], 0x3210)).  With the
+// selector in a register that every lane sets from its own winner, one pass serves all lanes of the group: a warp whose
+// lanes picked modules of one group runs one residue pass instead of one per module.  (Warps whose lanes agree keep the
+// specialised per-module pass: its shared-operand subtract is one instruction cheaper per word.)
+struct SelGroup {
+  std::vector<int> members;                       // indices into the module list
+  int wa[kMaxL / 4], wb[kMaxL / 4];               // operand words of word w
+  int cls[kMaxL / 4];                             // selector class of word w
+  std::vector<std::vector<unsigned>> cls_sel;     // per class: selector of every member
+};
+
+bool plan_sel_group(const std::vector<Module>& mods, const std::vector<int>& members, SelGroup* g) {
+  g->members = members;
+  g->cls_sel.clear();
+  const Module& m0 = mods[(size_t)members[0]];
+  for (int mi : members) {
+    const Module& m = mods[(size_t)mi];
+    if (m.family != Module::kCm || m.predictor == MPC_PRED_CONSEC || m.root != m0.root || m.cols != m0.cols || m.cxor != m0.cxor) return false;
+    for (int j = 0; j < L; j++)
+      if (m.xsrc[j] != m0.xsrc[j]) return false;
+  }
+  for (int w = 0; w < W; w++) {
+    std::vector<int> uni;
+    std::vector<std::vector<int>> srcs;
+    for (int mi : members) {
+      std::vector<int> ws;
+      int src[4];
+      if (!mods[(size_t)mi].pred_sel_form(w, &ws, src)) return false;
+      for (int x : ws)
+        if (std::find(uni.begin(), uni.end(), x) == uni.end()) uni.push_back(x);
+      srcs.push_back(std::vector<int>(src, src + 4));
+    }
+    if (uni.size() > 2) return false;
+    g->wa[w] = uni[0];
+    g->wb[w] = uni.size() == 2 ? uni[1] : uni[0];
+    std::vector<unsigned> sels;
+    for (auto& sv : srcs) {
+      unsigned sel = 0;
+      for (int q = 0; q < 4; q++) sel |= ((unsigned)(sv[(size_t)q] % 4) + (sv[(size_t)q] / 4 == g->wa[w] ? 0u : 4u)) << (4 * q);
+      sels.push_back(sel);
+    }
+    auto it = std::find(g->cls_sel.begin(), g->cls_sel.end(), sels);
+    if (it == g->cls_sel.end()) { g->cls_sel.push_back(sels); it = g->cls_sel.end() - 1; }
+    g->cls[w] = (int)(it - g->cls_sel.begin());
+  }
+  return g->cls_sel.size() <= 4;  // selector registers per lane
+}
+
+void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay, const SelGroup* grp = nullptr, int grp_id = 0) {
+  if (grp) {
+    std::string params;
+    for (size_t c = 0; c < grp->cls_sel.size(); c++) params += fmt(", uint32_t s%d", (int)c);
+    out.push_back(fmt("__device__ __forceinline__ void full_g%d(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq%s) {", grp_id, params.c_str()));
+  } else
   out.push_back(fmt("__device__ __forceinline__ void full_%d(const uint32_t (&x)[32], uint32_t (&c)[32], uint32_t& sa, uint32_t& sq) {", m.idx));
   out.push_back("  uint32_t g[32];");
   out.push_back("  uint32_t sa0 = 0, sa1 = 0, sa2 = 0, sa3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;  // four short chains instead of one long one");
@@ -388,6 +457,8 @@ void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay) {
   out.push_back("#pragma unroll");
   out.push_back(fmt("  for (int i = 0; i < %d; i++) ah[i] = x[i] | 0x80808080u;  // only the words a plain-copy predictor uses survive", W));
   for (int w = 0; w < W; w++) {
+    if (grp) out.push_back("  { " + m.residue_stmts(w, "r", false, fmt("prmt(x[%d], x[%d], s%d)", grp->wa[w], grp->wb[w], grp->cls[w])));
+    else
     out.push_back("  { " + m.residue_stmts(w, "r", true));
     if (w == 0) {
       // MAE/MSE run over all line positions (ResidueModule.cpp:43-73): the residue line holds the root byte itself at
@@ -962,6 +1033,36 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     out.push_back("");
   }
   if (t.pm2) emit_pm2_shared(mods, out);
+  // selector groups (see plan_sel_group): merged winner passes for warps whose lanes picked different modules of a group
+  std::vector<SelGroup> groups;
+  std::vector<int> group_of(mods.size(), -1);
+  {
+    const char* eg = getenv("MPC_SPEC_SELGROUP");
+    if (!t.pm2 && !t.fused_encode && !(eg && eg[0] == '0')) {
+      for (size_t i = 0; i < mods.size(); i++) {
+        if (group_of[i] >= 0) continue;
+        std::vector<int> members{(int)i};
+        SelGroup g, tryg;
+        for (size_t j = i + 1; j < mods.size(); j++) {
+          if (group_of[j] >= 0) continue;
+          std::vector<int> cand = members;
+          cand.push_back((int)j);
+          if (plan_sel_group(mods, cand, &tryg)) { members = cand; g = tryg; }
+        }
+        if (members.size() >= 2) {
+          for (int mi : members) group_of[(size_t)mi] = (int)groups.size();
+          groups.push_back(g);
+        }
+      }
+    }
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+      std::vector<std::string> names;
+      for (int mi : groups[gi].members) names.push_back(std::to_string(mods[(size_t)mi].idx));
+      out.push_back(fmt("// ---- selector group %d: modules %s share one winner pass in warps whose lanes picked different winners ----", (int)gi, join(names, ", ").c_str()));
+      emit_full(mods[(size_t)groups[gi].members[0]], out, t.lut_xor, lay, &groups[gi], (int)gi);
+      out.push_back("");
+    }
+  }
   out.push_back("struct Cfg {");
   out.push_back(fmt("  static constexpr int kLineBytes = %d;  // a thread holds 128 bytes = 128 / kLineBytes consecutive lines", L));
   out.push_back(fmt("  static constexpr int kWords = %d;", W));
@@ -1040,8 +1141,28 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     out.push_back("    (void)uniform;");
   }
   out.push_back("    int fam = 0;");
+  std::string else_prefix = "    ";
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const SelGroup& g = groups[gi];
+    std::vector<std::string> tests;
+    for (int mi : g.members) tests.push_back(fmt("best == %d", mods[(size_t)mi].idx));
+    out.push_back(else_prefix + "if (" + join(tests, " || ") + ") {  // one pass for the group, every lane with its own selectors");
+    std::string args;
+    for (size_t c = 0; c < g.cls_sel.size(); c++) {
+      std::string e = fmt("0x%04xu", g.cls_sel[c].back());
+      for (int k = (int)g.members.size() - 2; k >= 0; k--) e = fmt("(best == %d ? 0x%04xu : %s)", mods[(size_t)g.members[(size_t)k]].idx, g.cls_sel[c][(size_t)k], e.c_str());
+      out.push_back(fmt("      const uint32_t s%d = %s;", (int)c, e.c_str()));
+      args += fmt(", s%d", (int)c);
+    }
+    const int fid = (int)(std::find(fams.begin(), fams.end(), fam_of(mods[(size_t)g.members[0]])) - fams.begin());
+    out.push_back(fmt("      full_g%d(x, c, sa, sq%s); fam = %d;", (int)gi, args.c_str(), fid));
+    out.push_back("    } else");
+    else_prefix = "    ";
+  }
   out.push_back("    switch (best) {");
-  for (auto& m : mods) {
+  for (size_t i = 0; i < mods.size(); i++) {
+    const Module& m = mods[i];
+    if (group_of[i] >= 0) continue;
     const int fid = (int)(std::find(fams.begin(), fams.end(), fam_of(m)) - fams.begin());
     if (t.fused_encode) out.push_back(fmt("      case %d: full_%d(x, c, sa, sq); return %s;", m.idx, m.idx, call(fams[(size_t)fid]).c_str()));
     else out.push_back(fmt("      case %d: full_%d(x, c, sa, sq); fam = %d; break;", m.idx, m.idx, fid));
