@@ -17,6 +17,8 @@ constexpr unsigned long long kHistOff = 2 * kK;
 // the kernels form both indices of a word of two rows with one IDP.2A each (dot products with (260, 1)).
 constexpr unsigned kRowLutSkew = 260;
 constexpr unsigned kRowLutBytes = 66560;  // >= 260 * 255 + 255 + 1, a multiple of 16
+// Per-warp deferral buffer of the plane-major kernels (mpc_spec.cuh): 32 blocks of 128 bytes + their indices + their winners + a counter.
+constexpr unsigned kDeferBytesPerWarp = 32 * 128 + 32 * 4 + 32 * 4 + 128;
 // A CUtensorMap (128 bytes, 64-byte aligned) as the kernels see it: opaque, so that the NVRTC build needs no cuda.h.
 // Describes the dump as a [n_blocks][128 B] uint8 tensor with a 32 x 128 B box and the 128-byte swizzle
 // (make_tile_tmap, mpc_jit.cpp).

@@ -822,12 +822,19 @@ void emit_pm2_shared(const std::vector<Module>& mods, Lines& out) {
 // wins unscored while no earlier module has a zero row.
 void emit_pm2_select_encode(const std::vector<Module>& mods, Lines& out) {
   const int first = mods.front().idx, last = mods.back().idx;
-  out.push_back("  __device__ static __forceinline__ uint32_t select_encode(uint32_t (&x)[32], int& best, uint32_t& sa, uint32_t& sq, unsigned lanes) {");
+  out.push_back("  // preset >= 0: the winner is known (a block taken back from the warp's deferral buffer): winner pass only.  defer(best) may take");
+  out.push_back("  // a block whose winner is not the last module off this lane's hands (mpc_spec.cuh: it is finished later in a full batch of such");
+  out.push_back("  // blocks); the lane then returns kDeferred.");
+  out.push_back("  static constexpr uint32_t kDeferred = 0xffffffffu;");
+  out.push_back("  template <class Defer>");
+  out.push_back("  __device__ static __forceinline__ uint32_t select_encode(uint32_t (&x)[32], int& best, uint32_t& sa, uint32_t& sq, unsigned lanes, int preset, Defer&& defer) {");
   out.push_back("    uint32_t r[32];");
   out.push_back("    uint32_t bestz = 0u;");
+  out.push_back("    bool deferred = false;");
   out.push_back(fmt("    int k = %d;", first));
   out.push_back(fmt("    bool scoring = %s;", first == last ? "false" : "true"));
   if (first == last) out.push_back(fmt("    best = %d;", last));
+  out.push_back("    if (preset >= 0) { best = preset; k = preset; scoring = false; }");
   out.push_back("    for (;;) {");
   out.push_back("      // the block does not change between iterations, so the compiler would hoist every predictor gather of every module out of");
   out.push_back("      // the loop (and spill them); an empty asm per word makes the block opaque at the top of each iteration (no instruction)");
@@ -844,6 +851,7 @@ void emit_pm2_select_encode(const std::vector<Module>& mods, Lines& out) {
   out.push_back(fmt("      if (k == %d) {  // every module is scored: r holds the winner's residues only if the last module won with a complete pass", last));
   out.push_back("        scoring = false;");
   out.push_back(fmt("        if (best == %d && ze == %du) break;", last, NCH()));
+  out.push_back(fmt("        if (best != %d && defer(best)) { deferred = true; break; }", last));
   out.push_back("        k = best;");
   out.push_back("        continue;");
   out.push_back("      }");
@@ -851,6 +859,7 @@ void emit_pm2_select_encode(const std::vector<Module>& mods, Lines& out) {
   out.push_back(fmt("      if (k == %d && bestz == 0u) { best = %d; scoring = false; }  // the last module wins every tie", last, last));
   out.push_back("    }");
   out.push_back("    __syncwarp(lanes);  // one pass over the shared tail for the whole warp, whatever modules its lanes picked");
+  out.push_back("    if (deferred) return kDeferred;");
   out.push_back("    return pm2_tail(best, x, r, sa, sq);");
   out.push_back("  }");
 }
@@ -918,6 +927,13 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
     if (e2 && e2[0] == '0') t.pm2 = false;
   }
   bool has_bg = false;
+  {
+    const char* e3 = getenv("MPC_SPEC_DEFER");
+    // Measured on B200 (profiles/r02_defer.txt): it pays only where winners other than the last module are rare (P6 smooth +5 %,
+    // hash-mixed +4 %) and costs 5-10 % where they are not (ramp, sparse) or never occur (random: code size), so it is OFF unless
+    // MPC_SPEC_DEFER=1 asks.
+    t.defer = t.pm2 && cfg.line_size == 128 && mods.size() >= 2 && (e3 && e3[0] == '1');
+  }
   for (auto& m : mods) {
     if (m.family == Module::kPm) has_pm = true;
     else { has_cm = true; all_c = all_c && m.cxor; any_c = any_c || m.cxor; }
@@ -949,7 +965,7 @@ SpecTraits spec_traits(const mpc_config_pod& cfg) {
   // of the stage before the next copy), so cp.async stays the default.
   t.tma = t.stages == 1 && cfg.line_size == 128 && (e = getenv("MPC_SPEC_TMA")) && e[0] == '1';
   t.smem_bytes = (size_t)t.warps * t.stages * 4096 + (t.tma ? (size_t)((t.warps * 8 + 15) / 16) * 16 : 0) + 4 * ((((size_t)(cfg.num_modules + 1) * (8 * 128 + 32) + 4 * (cfg.num_modules + 1)) + 3) & ~(size_t)3) +
-                 (t.use_lut ? (size_t)kRowLutBytes : 0);
+                 (t.use_lut ? (size_t)kRowLutBytes : 0) + (t.defer ? (size_t)t.warps * kDeferBytesPerWarp + 128 : 0);
   // Regrouping queues (mpc_spec.cuh): one queue per PredComp module in the shared memory that is left (227 KiB per CTA on sm_100,
   // 1 KiB of it reserved by the driver); an entry is the block (128 B) + its index + a flag word.  At least two batches of 32 per
   // queue, else the kernel runs without them (MPC_SPEC_REGROUP=0 switches them off for A/B runs).
@@ -1082,6 +1098,7 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
   out.push_back(fmt("  static constexpr int kMinCtasPerSm = %d;  // __launch_bounds__: register budget 65536 / (threads * CTAs)", t.min_ctas));
   out.push_back(fmt("  static constexpr int kQueueCap = %d;  // entries per regrouping queue (one queue per PredComp module); 0 = no regrouping", t.queue_cap));
   out.push_back(fmt("  static constexpr bool kPm2 = %s;  // one residue pass per module + shared scoring / statistics / classifier (select_encode)", t.pm2 ? "true" : "false"));
+  out.push_back(fmt("  static constexpr bool kDefer = %s;  // per-warp deferral buffer for blocks whose winner is not the last module (pm2, 128-byte lines)", t.defer ? "true" : "false"));
   out.push_back("  __device__ static __forceinline__ uint32_t enc(int k) {  // encoding bits of cluster k-1, VPC.cpp:102-117");
   out.push_back("    switch (k) {");
   for (int k = 0; k <= n; k++) out.push_back(fmt("      case %d: return %du;", k, cfg.enc_bits[k]));
@@ -1096,7 +1113,9 @@ std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& n
     out.push_back("};");
     out.push_back("");
   } else {
-  out.push_back("  __device__ static __forceinline__ uint32_t select_encode(uint32_t (&)[32], int&, uint32_t&, uint32_t&, unsigned) { return 0u; }");
+  out.push_back("  static constexpr uint32_t kDeferred = 0xffffffffu;");
+  out.push_back("  template <class Defer>");
+  out.push_back("  __device__ static __forceinline__ uint32_t select_encode(uint32_t (&)[32], int&, uint32_t&, uint32_t&, unsigned, int, Defer&&) { return 0u; }");
   out.push_back("  // VPC.cpp:372-395: most leading zero rows wins, ties go to the later module");
   out.push_back("  __device__ static __forceinline__ void select(const uint32_t (&x)[32], int& best, uint32_t& bestz, unsigned lanes) {");
   out.push_back("    uint32_t z;");

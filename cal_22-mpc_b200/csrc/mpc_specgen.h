@@ -20,6 +20,7 @@ struct SpecTraits {
   int queue_cap = 0;             // entries per regrouping queue (mpc_spec.cuh), 0 = none
   bool fused_encode = false;     // every module's winner pass runs into its own copy of the row classifier
   bool adaptive_encode = false;  // fused passes for warps whose lanes agree on the module, the shared classifier otherwise
+  bool defer = false;            // pm2: per-warp deferral buffer (blocks whose winner is not the last module are finished in full batches)
   bool pm2 = false;              // all modules plane-major with one scan family: one residue pass per module, shared scoring / statistics / classifier code
   size_t smem_bytes = 0;         // dynamic shared memory of one CTA
 };

@@ -118,6 +118,15 @@ def test_arbitrary_scan_table_jit_kernels_match_oracle(mpcb, seed, table, L):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_plane_major_deferral_buffer_variant_matches_oracle(mpcb, monkeypatch, seed):
+    """MPC_SPEC_DEFER=1 (profiles/r02_defer.txt: measured, off by default): blocks whose winner is not the last module are parked in a
+    per-warp buffer and finished in batches -- every block still exactly once, ragged tail included"""
+    monkeypatch.setenv("MPC_SPEC_DEFER", "1")
+    check_jit_config(mpcb, shared_scan_pm_config(400 + seed, 128), seed, 128, n=5003)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("L", [32, 64, 128])
 @pytest.mark.parametrize("seed", range(4))
 def test_shared_scan_plane_major_jit_kernels_match_oracle(mpcb, seed, L):
@@ -179,9 +188,10 @@ def test_tma_variant_compiles_with_nvrtc(mpcb, monkeypatch):
 
 
 @pytest.mark.parametrize("flags", [{"MPC_SPEC_REGROUP": "1"}, {"MPC_SPEC_REGROUP": "1", "MPC_SPEC_FUSED": "0"}, {"MPC_SPEC_ADAPTIVE": "0"},
-                                   {"MPC_SPEC_FUSED": "1"}])
+                                   {"MPC_SPEC_FUSED": "1"}, {"MPC_SPEC_DEFER": "1"}, {"MPC_SPEC_SELGROUP": "0"}, {"MPC_SPEC_PM2": "0"}])
 def test_generation_variants_compile_with_nvrtc(mpcb, monkeypatch, flags):
-    """The generation-time switches of the specialised kernel (regrouping queues, fused / adaptive / shared winner pass)."""
+    """The generation-time switches of the specialised kernel (regrouping queues, fused / adaptive / shared winner pass, deferral buffer,
+    selector groups off, first-generation plane-major form)."""
     for k, v in flags.items():
         monkeypatch.setenv(k, v)
     for cfg in ("F4", "P6"):
