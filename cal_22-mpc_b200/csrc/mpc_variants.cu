@@ -40,6 +40,19 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long bits = 0;
+  // FPC (64 registers: room to spare): per-thread counters -- a block's eight 8-bit counters (<= 32 each) are added into one 64-bit
+  // word, which is unpacked into 32-bit registers every seventh block (7 x 32 < 256): a couple of instructions per block instead of eight
+  // warp reductions and atomics, the warp reductions happen once after the last tile (+7 % on the hash-mixed dump).  BDI and BPC sit at
+  // 103 / 126 registers: the ten extra live registers spill there (measured -17 % / -29 %), so they aggregate per tile as before.
+  constexpr bool kThreadCounters = ALG == MPC_ALG_FPC;
+  unsigned long long acc8 = 0;
+  uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, in_acc8 = 0;
+  auto unpack = [&]() {
+#pragma unroll
+    for (int p = 0; p < 8; p++) acc[p] += (uint32_t)(acc8 >> (8 * p)) & 0xffu;
+    acc8 = 0;
+    in_acc8 = 0;
+  };
   constexpr int S = 32 / W;  // lines per thread
   // the tile loader works on 128-byte units: n_blocks lines = ceil(n_blocks / S) units, the last one possibly partial
   tile::for_each_block(lines, (n_blocks + S - 1) / S, s_stage + warp * tile::kStages * 256, kWarps,
@@ -66,8 +79,10 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
     if (!valid) { size = 0; packed = 0; extra = 0; }
     if (valid && sizes) sizes[blk] = (uint16_t)size;
     bits += size;
-    // warp-aggregate the small counters, one shared atomic per counter per tile
-    if (ALG == MPC_ALG_BDI) {
+    if (kThreadCounters) {
+      acc8 += packed;
+      if (++in_acc8 == 7) unpack();
+    } else if (ALG == MPC_ALG_BDI) {  // warp-aggregate the small counters, one shared atomic per counter per tile
 #pragma unroll
       for (int s = 0; s < 9; s++) {
         const uint32_t c = __popc(__ballot_sync(0xffffffffu, (packed >> (4 * s)) & 1ull));
@@ -79,13 +94,19 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
         const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)((packed >> (8 * p)) & 0xffull));
         if (lane == 0 && c) atomicAdd(&s_cnt[1 + p], (unsigned long long)c);
       }
-      if (ALG == MPC_ALG_BPC) {
-        const uint32_t c = __reduce_add_sync(0xffffffffu, extra);
-        if (lane == 0 && c) atomicAdd(&s_cnt[1 + 7], (unsigned long long)c);  // counts[7] = TotalWords
-      }
+      const uint32_t c = __reduce_add_sync(0xffffffffu, extra);
+      if (lane == 0 && c) atomicAdd(&s_cnt[1 + 7], (unsigned long long)c);  // counts[7] = TotalWords
     }
    }  // sub-lines
   }, n_blocks * (uint64_t)(W / 4));
+  if (kThreadCounters) {
+    unpack();
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+      const uint32_t c = __reduce_add_sync(0xffffffffu, acc[p]);
+      if (lane == 0 && c) atomicAdd(&s_cnt[1 + p], (unsigned long long)c);
+    }
+  }
   // per-thread bit totals -> warp -> CTA -> global
   for (int o = 16; o; o >>= 1) bits += __shfl_down_sync(0xffffffffu, bits, o);
   if (lane == 0 && bits) atomicAdd(&s_cnt[0], bits);
