@@ -285,6 +285,23 @@ int ensure_stages(mpc_ctx* ctx) {
     return fail(ctx, MPC_E_CUDA, "allocating the host-submit stages failed: %s", cudaGetErrorString(e));
   }
   ctx->stages_ready = true;
+  // The first launch of a kernel loads its code onto the device (CUDA loads modules lazily: ~5 ms for the specialised kernels,
+  // measured as the difference to CUDA_MODULE_LOADING=EAGER).  Pay that here, with the other one-off set-up costs, instead of in the
+  // first chunk of the first submission: one tile of zeroes into a scratch statistics vector that is thrown away.
+  {
+    uint64_t* scratch = nullptr;
+    Stage& st = ctx->stage[0];
+    if (cudaMalloc(&scratch, mpc::kStatsWords * sizeof(uint64_t)) == cudaSuccess) {
+      cudaMemsetAsync(scratch, 0, mpc::kStatsWords * sizeof(uint64_t), st.stream);
+      cudaMemsetAsync(st.d_lines, 0, 4096, st.stream);
+      std::swap(ctx->d_stats, scratch);
+      const int rc = launch(ctx, st.d_lines, 4096 / (uint64_t)ctx->cfg.line_size, nullptr, st.stream, 1);
+      std::swap(ctx->d_stats, scratch);
+      cudaStreamSynchronize(st.stream);
+      cudaFree(scratch);
+      if (rc != MPC_OK) { free_stages(ctx); return rc; }
+    }
+  }
   return MPC_OK;
 }
 
