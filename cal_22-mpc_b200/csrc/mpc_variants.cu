@@ -17,6 +17,11 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCounters = 16;  // device layout: [0] compressed bits, [1..16] counters
+#ifndef MPC_VARIANT_MIN_CTAS
+// CTAs per SM the register allocation aims for (64 KiB of tile stages each: three fit).  Measured 2 -> 3 on the 1 GiB dumps: BPC (126 -> 85
+// registers, 84 bytes spilled) hash-mixed 1 200 -> 1 382 GB/s, by region 1 746 -> 1 845; BDI 748 -> 784 / 2 083 -> 2 073; FPC (64 registers) equal.
+#define MPC_VARIANT_MIN_CTAS 3
+#endif
 
 // warp-wide votes for mpcvar::bdi_block_with: every lane calls the maker, the lanes that run the checks vote among themselves
 struct WarpVote {
@@ -30,7 +35,7 @@ struct MakeWarpVote {
 // W = words per line: a thread holds 128 bytes = 32 / W consecutive lines (32-, 64- and 128-byte lines; the reference's
 // models take any line size, BDI.cpp:108-201, FPC.cpp:7-87, BPC.cpp:20-185)
 template <int ALG, int W>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MPC_VARIANT_MIN_CTAS)
 variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __restrict__ sizes,
                unsigned long long* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
