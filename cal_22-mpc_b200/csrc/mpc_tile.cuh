@@ -21,7 +21,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // Calls body(x, blk, valid) for every block of the dump, one block per lane per tile; tiles are dealt round-robin
 // to the warps of the grid.  `my_stage` = this warp's 2 x 4 KiB of shared memory.
-template <class Body>
+// STAGES = 2: the next tile is requested before the current one is read (two 4 KiB stages per warp); STAGES = 1: it is requested right
+// after the current tile sits in registers (the registers are the second buffer: half the shared memory, more CTAs per SM).
+template <int STAGES = kStages, class Body>
 // `valid_chunks` (16-byte chunks of the dump that exist; 0 = n_blocks * 8) bounds the reads when the last 128-byte unit is
 // partial (lines of 32 / 64 bytes); the missing chunks arrive as zeros.
 __device__ __forceinline__ void for_each_block(const uint4* __restrict__ lines, uint64_t n_blocks, uint4* my_stage,
@@ -55,7 +57,7 @@ __device__ __forceinline__ void for_each_block(const uint4* __restrict__ lines, 
   if (t < n_tiles) issue(t, 0);
   for (; t < n_tiles; t += total_warps) {
     const uint64_t next = t + total_warps;
-    if (next < n_tiles) {
+    if (STAGES == 2 && next < n_tiles) {
       issue(next, stage ^ 1);
       cp_async_wait<1>();
     } else {
@@ -69,9 +71,10 @@ __device__ __forceinline__ void for_each_block(const uint4* __restrict__ lines, 
       x[4 * j] = q.x; x[4 * j + 1] = q.y; x[4 * j + 2] = q.z; x[4 * j + 3] = q.w;
     }
     __syncwarp();  // the stage is overwritten by the prefetch issued in the next iteration
+    if (STAGES == 1 && next < n_tiles) issue(next, 0);
     const uint64_t blk = t * kTileBlocks + lane;
     body(x, blk, blk < n_blocks);
-    stage ^= 1;
+    if (STAGES == 2) stage ^= 1;
   }
 }
 

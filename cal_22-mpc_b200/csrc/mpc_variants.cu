@@ -17,11 +17,15 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCounters = 16;  // device layout: [0] compressed bits, [1..16] counters
-#ifndef MPC_VARIANT_MIN_CTAS
-// CTAs per SM the register allocation aims for (64 KiB of tile stages each: three fit).  Measured 2 -> 3 on the 1 GiB dumps: BPC (126 -> 85
-// registers, 84 bytes spilled) hash-mixed 1 200 -> 1 382 GB/s, by region 1 746 -> 1 845; BDI 748 -> 784 / 2 083 -> 2 073; FPC (64 registers) equal.
-#define MPC_VARIANT_MIN_CTAS 3
-#endif
+// Per algorithm: CTAs per SM the register allocation aims for and tile stages per warp (mpc_tile.cuh; one stage = the registers are the
+// second buffer, 32 instead of 64 KiB of shared memory per CTA).  Measured on the 1 GiB hash-mixed / region-mixed dumps (GB/s):
+//                 2 stages, 2 CTAs   2 stages, 3 CTAs   1 stage, 3 CTAs   1 stage, 4 CTAs
+//   BDI (103 regs)   748 / 2 083        782 / 2 131        748 / 1 976       684 / 1 878
+//   FPC (64 regs)  1 645 / 2 511      1 648 / 2 529      1 674 / 2 572     1 801 / 2 582
+//   BPC (126 regs) 1 200 / 1 746      1 370 / 1 862      1 382 / 1 904     1 281 / 1 644
+template <int ALG> struct VariantTune { static constexpr int kMinCtas = 3, kStages = 2; };           // BDI
+template <> struct VariantTune<MPC_ALG_FPC> { static constexpr int kMinCtas = 4, kStages = 1; };
+template <> struct VariantTune<MPC_ALG_BPC> { static constexpr int kMinCtas = 3, kStages = 1; };
 
 // warp-wide votes for mpcvar::bdi_block_with: every lane calls the maker, the lanes that run the checks vote among themselves
 struct WarpVote {
@@ -35,7 +39,7 @@ struct MakeWarpVote {
 // W = words per line: a thread holds 128 bytes = 32 / W consecutive lines (32-, 64- and 128-byte lines; the reference's
 // models take any line size, BDI.cpp:108-201, FPC.cpp:7-87, BPC.cpp:20-185)
 template <int ALG, int W>
-__global__ void __launch_bounds__(kThreads, MPC_VARIANT_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, VariantTune<ALG>::kMinCtas)
 variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __restrict__ sizes,
                unsigned long long* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -60,7 +64,8 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
   };
   constexpr int S = 32 / W;  // lines per thread
   // the tile loader works on 128-byte units: n_blocks lines = ceil(n_blocks / S) units, the last one possibly partial
-  tile::for_each_block(lines, (n_blocks + S - 1) / S, s_stage + warp * tile::kStages * 256, kWarps,
+  constexpr int kVariantStages = VariantTune<ALG>::kStages;
+  tile::for_each_block<kVariantStages>(lines, (n_blocks + S - 1) / S, s_stage + warp * kVariantStages * 256, kWarps,
                        [&](const uint32_t (&x128)[32], uint64_t unit, bool) {
 #pragma unroll
    for (int sub = 0; sub < S; sub++) {
@@ -129,7 +134,7 @@ int vfail(int code, const char* what, cudaError_t e) {
 template <int ALG, int W>
 cudaError_t launch_variant_w(const uint8_t* d_lines, uint64_t n, uint16_t* d_sizes, unsigned long long* d_stats, int sms,
                              cudaStream_t s) {
-  const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
+  const size_t smem = (size_t)kWarps * VariantTune<ALG>::kStages * tile::kTileBytes;
   cudaError_t e = cudaFuncSetAttribute(variant_kernel<ALG, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
