@@ -5,6 +5,14 @@
 // byte histograms (all lines; lines that are neither all-zero nor word-repeating, Pattern.h:96-125) from which the
 // report computes two entropies.  One block per thread through the tile loader shared with the other variants.
 //
+// Byte histogram of the non-trivial lines: 128 increments per line.  Shared-memory atomics cost two cycles per LANE on this
+// hardware whatever the addresses are (64 cycles per warp instruction: 8 192 cycles per tile of 32 lines, the whole kernel at
+// 0.1-0.2 TB/s), plain shared-memory loads and stores one cycle per conflict-free WARP instruction.  So every lane keeps its own
+// counters and updates them without atomics: a warp owns an 8 KiB table of 8-bit counters, counter (byte value v, lane l) at
+// byte 32 v + l -- no two lanes ever touch the same counter, and only lanes of the same quad can meet in a bank.  A counter that
+// is about to wrap passes 256 on to the CTA's 32-bit table (one atomic per 256 increments); the warp sums its table into
+// that table when it has run out of tiles.
+//
 // Temporal locality (Pattern.cpp:101-107, LRU.h:17-56): a line counts when an identical line is in the cache.  The
 // reference never promotes a hit and inserts only on a miss, so the cache is a FIFO set of the last C = 2^24 - 1
 // distinct lines that missed.  While the dump holds at most C distinct lines nothing is ever evicted and the count is
@@ -29,6 +37,8 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
+constexpr int kPatStages = 1;             // tile stages per warp (the registers are the second buffer)
+constexpr uint32_t kLaneTableBytes = 256 * 32;  // per warp: one 8-bit counter per (byte value, lane)
 // device counters: [0] zero lines [1] repeat lines [2] undefined lines [3..8] lines per pattern [9..14] immediates per
 // pattern [15] duplicate lines [16] hash collisions ; then two 256-bin byte histograms (trivial lines / other lines)
 constexpr int kCnt = 17;
@@ -42,6 +52,52 @@ int pfail(int code, const std::string& what) { g_perr = what; return code; }
     if (e__ != cudaSuccess) return pfail(MPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
+// The four bytes of one line word into this lane's 8-bit counters.  `table` = shared-memory address of the warp's table (8 KiB
+// aligned) + lane, so that a counter's address is one LOP3: table | 32 * byte value, the latter being the word shifted so that the
+// byte sits at bits 5..12 (shifts on the FMA pipe).  The loads and stores of equal bytes hit the same counter and stay in program
+// order; a counter that wrapped to 0 (one test per word) hands 256 to the CTA's 32-bit bin of its byte value.
+__device__ __forceinline__ uint32_t lane_count(uint32_t addr) {
+  uint32_t c;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(addr) : "memory");
+  c += 1u;
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(c) : "memory");
+  return c;
+}
+#ifndef MPC_PAT_LAYOUT
+#define MPC_PAT_LAYOUT 0
+#endif
+// shared-memory address of this lane's counter of byte k of the word v; bin = the byte value the address stands for
+#if MPC_PAT_LAYOUT == 0
+// counter (value b, lane l) at byte 32 b + l: one shift (FMA pipe) and one LOP3 per byte; lanes of one quad that hold different
+// values with equal b mod 4 meet in a bank (2- to 4-way on random bytes, none on the equal bytes of structured data)
+template <int K>
+__device__ __forceinline__ uint32_t lane_counter(uint32_t v, uint32_t table) {
+  const uint32_t s = K == 0 ? (v << 5) : mpcdev::shr_fma(v, 8 * K - 5);
+  return table | (s & 0x1fe0u);
+}
+__device__ __forceinline__ uint32_t counter_bin(uint32_t addr) { return (addr >> 5) & 0xffu; }
+#else
+// counter (value b, lane l) at byte 128 (b >> 2) + 4 l + (b & 3): the bank is the lane whatever the values are, at the price of a
+// second shift and LOP3 per byte.  `table` = table base + 4 * lane.
+template <int K>
+__device__ __forceinline__ uint32_t lane_counter(uint32_t v, uint32_t table) {
+  const uint32_t s = K == 0 ? (v << 5) : mpcdev::shr_fma(v, 8 * K - 5);
+  const uint32_t t = K == 0 ? v : mpcdev::shr_fma(v, 8 * K);
+  return (s & 0x1f80u) | ((t & 3u) | table);
+}
+__device__ __forceinline__ uint32_t counter_bin(uint32_t addr) { return ((addr >> 5) & 0xfcu) | (addr & 3u); }
+#endif
+__device__ __forceinline__ void lane_count_word(uint32_t v, uint32_t table, uint32_t* s_bins) {
+  const uint32_t a0 = lane_counter<0>(v, table), a1 = lane_counter<1>(v, table), a2 = lane_counter<2>(v, table), a3 = lane_counter<3>(v, table);
+  const uint32_t c0 = lane_count(a0), c1 = lane_count(a1), c2 = lane_count(a2), c3 = lane_count(a3);
+  if ((c0 | c1 | c2 | c3) & 0x100u) {
+    if (c0 == 256u) atomicAdd(&s_bins[counter_bin(a0)], 256u);
+    if (c1 == 256u) atomicAdd(&s_bins[counter_bin(a1)], 256u);
+    if (c2 == 256u) atomicAdd(&s_bins[counter_bin(a2)], 256u);
+    if (c3 == 256u) atomicAdd(&s_bins[counter_bin(a3)], 256u);
+  }
+}
+
 // W = words per line: a thread holds 128 bytes = 32 / W consecutive lines (the analysis takes any line size, Pattern.cpp:6-75)
 template <int W>
 __global__ void __launch_bounds__(kThreads)
@@ -53,10 +109,17 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
   __shared__ uint32_t s_hist[512];  // [0..255] bytes of all-zero / word-repeating lines, [256..511] bytes of the others
   if (threadIdx.x < kCnt) s_cnt[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < 512; i += kThreads) s_hist[i] = 0;
+  // per-warp tables of per-lane 8-bit byte counters behind the tile stages, 8 KiB aligned in the shared-memory window
+  const uint32_t stages_end = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)(kWarps * kPatStages * tile::kTileBytes);
+  const uint32_t tables_at = (stages_end + (kLaneTableBytes - 1u)) & ~(kLaneTableBytes - 1u);
+  uint32_t* s_tables = reinterpret_cast<uint32_t*>(smem_raw + (tables_at - (uint32_t)__cvta_generic_to_shared(smem_raw)));
+  for (int i = threadIdx.x; i < kWarps * (kLaneTableBytes / 4); i += kThreads) s_tables[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t my_table = tables_at + (uint32_t)warp * kLaneTableBytes + (uint32_t)lane * (MPC_PAT_LAYOUT == 0 ? 1u : 4u);
+  uint32_t* s_bins = s_hist + 256;
   constexpr int S = 32 / W;
-  tile::for_each_block(lines, (n_blocks + S - 1) / S, s_stage + warp * tile::kStages * 256, kWarps,
+  tile::for_each_block<kPatStages>(lines, (n_blocks + S - 1) / S, s_stage + warp * kPatStages * 256, kWarps,
                        [&](const uint32_t (&x128)[32], uint64_t unit, bool) {
 #pragma unroll
    for (int sub = 0; sub < S; sub++) {
@@ -82,10 +145,7 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
       for (int k = 0; k < 4; k++) atomicAdd(&s_hist[(x[0] >> (8 * k)) & 0xffu], (uint32_t)W);
     } else if (valid) {
 #pragma unroll
-      for (int i = 0; i < W; i++) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) atomicAdd(&s_hist[256 + ((x[i] >> (8 * k)) & 0xffu)], 1u);
-      }
+      for (int i = 0; i < W; i++) lane_count_word(x[i], my_table, s_bins);
     }
     // warp-aggregated line counters
     const uint32_t cz = __popc(__ballot_sync(0xffffffffu, is_zero)), cr = __popc(__ballot_sync(0xffffffffu, is_rep));
@@ -106,6 +166,23 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
     }
    }  // sub-lines
   }, n_blocks * (uint64_t)(W / 4));
+  // this warp's counters into the CTA's bins: lane l sums the 32 lane counters (8 words) of values l, l + 32, ...
+  __syncwarp();
+  {
+    const uint32_t* t = s_tables + warp * (kLaneTableBytes / 4);
+#pragma unroll 1
+    for (int v = lane; v < 256; v += 32) {
+      uint32_t sum = 0;
+#if MPC_PAT_LAYOUT == 0
+#pragma unroll
+      for (int j = 0; j < 8; j++) sum = __dp4a(t[v * 8 + ((j + (lane >> 2)) & 7)], 0x01010101u, sum);
+#else
+#pragma unroll 8
+      for (int j = 0; j < 32; j++) sum += (t[(v >> 2) * 32 + ((j + (lane >> 2)) & 31)] >> (8 * (v & 3))) & 0xffu;
+#endif
+      if (sum) atomicAdd(&s_bins[v], sum);
+    }
+  }
   __syncthreads();
   if (threadIdx.x < kCnt && s_cnt[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_cnt[threadIdx.x]);
   for (int i = threadIdx.x; i < 512; i += kThreads)
@@ -232,7 +309,7 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
   EventPair ev;
   cudaEventRecord(ev.a, 0);
   if (n) {
-    const size_t smem = (size_t)kWarps * tile::kStages * tile::kTileBytes;
+    const size_t smem = (size_t)kWarps * kPatStages * tile::kTileBytes + (size_t)(kWarps + 1) * kLaneTableBytes;  // + alignment slack
     auto launch = [&](auto kernel, uint64_t lines_per_unit) -> cudaError_t {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
