@@ -113,6 +113,36 @@ MPC_HD uint32_t add_u8x4(uint32_t a, uint32_t b) {
   return t ^ ((a ^ b) & H);
 }
 
+// ---- (a - b) mod 256 per byte in 16-bit lanes, for predicted bytes that are SHIFTED line bytes (WeightBasePredictor) ----------
+// sub_u8x4 costs four ALU-pipe instructions per word plus whatever assembles b (masks of the shifted bytes).  Here the line word
+// is split once into its even bytes [a0, 1, a2, 0] and its odd bytes [0, a1, 1, a3] (one PRMT each; the 1s are borrow guards),
+// every predicted byte is SUBTRACTED in place by a multiply-add on the FMA pipe (value * -2^k + lanes: the multiplier is the shift
+// and the byte position at once), and one LOP3 puts the two halves together.  A term must be exact in its own byte and zero below
+// it; what it leaves above the byte is harmless in byte 3 of the even half (discarded) and beyond bit 31.
+MPC_HD uint32_t lanes_even(uint32_t a) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, 1u, 0x5240u);
+#else
+  return (a & 0x00ff00ffu) | 0x00000100u;
+#endif
+}
+MPC_HD uint32_t lanes_odd(uint32_t a) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, 1u, 0x3415u);
+#else
+  return (a & 0xff00ff00u) | 0x00010000u;
+#endif
+}
+MPC_HD uint32_t lanes_merge(uint32_t even, uint32_t odd) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;  // one bit select (written with two masks ptxas emits two LOP3)
+  asm("lop3.b32 %0, %1, %2, 0x00ff00ff, 0xe4;" : "=r"(d) : "r"(even), "r"(odd));
+  return d;
+#else
+  return (even & 0x00ff00ffu) | (odd & 0xff00ff00u);
+#endif
+}
+
 // ---- bit-plane XOR folded into the byte domain ------------------------------------------------------
 // BitplaneModule (plane b = bit 7-b of the residue byte, BitplaneModule.cpp:25-36) followed by
 // XORModule (XORModule.cpp:9-20).  `keep` has 0xff in every byte lane that must stay untouched

@@ -113,6 +113,56 @@ std::string gather_expr(const std::string& arr, const int (&srcs)[4]) {
   return finish(fmt("prmt(%s, %s, 0x%04xu)", partial(first).c_str(), partial(second).c_str(), sel));
 }
 
+// Canonical layout of a plane-major scan (mpc_spec.cuh, pm_classify): c[16 h + k], byte lane q = k-th column (scan order) of column
+// chunk 4 h + q.  One c word at a time that is a gather from four residue words = three PRMTs.  But columns a whole number of
+// words apart give c words that are the SAME byte position of the same four residue words (A, B, C, D) -- the rows of a 4 x 4 byte
+// transpose, which takes two PRMT stages: (A, B) and (C, D) interleaved in their low / high halves, then the pairs combined; 8 PRMTs
+// for 4 words instead of 12, 7 instead of 9 for three of them (P6: 68 instead of 96 per block).  Words that do not fit keep the gather.
+// `transposes` = false: gathers only (the per-module winner passes of configs that mix scan families run at their register limit: measured
+// 1-2 % slower on E5 with the transposes' temporaries).
+void emit_pm_canonical(const std::vector<int>& cols, const char* arr, Lines& out, bool transposes = true) {
+  const int nh = (NCH() + 3) / 4;
+  std::vector<std::vector<int>> srcs((size_t)16 * nh, std::vector<int>(4, -1));
+  for (int h = 0; h < nh; h++)
+    for (int k = 0; k < 16; k++)
+      for (int q = 0; q < 4; q++) srcs[16 * h + k][q] = (4 * h + q) < NCH() ? cols[16 * (4 * h + q) + k] : -1;  // lines of 32 bytes: two chunks, two zero lanes
+  const char* env = getenv("MPC_SPEC_TRANSPOSE4");
+  const bool on = transposes && !(env && env[0] == '0');
+  std::map<std::vector<int>, std::map<int, int>> groups;  // (A, B, C, D) -> byte position -> c index
+  if (on)
+    for (int i = 0; i < 16 * nh; i++) {
+      const std::vector<int>& s4 = srcs[i];
+      if (s4[0] < 0 || s4[1] < 0 || s4[2] < 0 || s4[3] < 0) continue;
+      const int b = s4[0] % 4;
+      if (s4[1] % 4 != b || s4[2] % 4 != b || s4[3] % 4 != b) continue;
+      std::vector<int> words = {s4[0] / 4, s4[1] / 4, s4[2] / 4, s4[3] / 4};
+      if (std::set<int>(words.begin(), words.end()).size() != 4) continue;
+      if (groups[words].count(b)) continue;  // a duplicate column: the gather below serves it
+      groups[words][b] = i;
+    }
+  std::set<int> done;
+  int gi = 0;
+  for (auto& g : groups) {
+    const std::map<int, int>& by_b = g.second;
+    const bool lo = by_b.count(0) || by_b.count(1), hi = by_b.count(2) || by_b.count(3);
+    if ((int)by_b.size() + 2 * ((lo ? 1 : 0) + (hi ? 1 : 0)) >= 3 * (int)by_b.size()) continue;  // no cheaper than the gathers
+    const std::vector<int>& w = g.first;
+    if (lo) out.push_back(fmt("  const uint32_t tl%d = prmt(%s[%d], %s[%d], 0x5140u), ul%d = prmt(%s[%d], %s[%d], 0x5140u);", gi, arr, w[0], arr, w[1], gi, arr, w[2], arr, w[3]));
+    if (hi) out.push_back(fmt("  const uint32_t th%d = prmt(%s[%d], %s[%d], 0x7362u), uh%d = prmt(%s[%d], %s[%d], 0x7362u);", gi, arr, w[0], arr, w[1], gi, arr, w[2], arr, w[3]));
+    for (auto& bi : by_b) {
+      const int b = bi.first;
+      out.push_back(fmt("  c[%d] = prmt(t%c%d, u%c%d, 0x%04xu);", bi.second, b < 2 ? 'l' : 'h', gi, b < 2 ? 'l' : 'h', gi, (b & 1) ? 0x7632u : 0x5410u));
+      done.insert(bi.second);
+    }
+    gi++;
+  }
+  for (int i = 0; i < 16 * nh; i++) {
+    if (done.count(i)) continue;
+    const int s4[4] = {srcs[i][0], srcs[i][1], srcs[i][2], srcs[i][3]};
+    out.push_back(fmt("  c[%d] = %s;", i, gather_expr(arr, s4).c_str()));
+  }
+}
+
 // ---- module model --------------------------------------------------------------------------------------------------
 struct Module {
   int idx = 0;
@@ -235,6 +285,54 @@ struct Module {
     return base;
   }
 
+  // Residue word w of a shifting (Weight) predictor in 16-bit lanes (mpc_device.cuh: lanes_even / lanes_odd / lanes_merge): the line
+  // word is split into its even and odd bytes and every predicted byte -- byte sb of line word sw, shifted by s -- is subtracted in
+  // place by one multiply-add on the FMA pipe whose multiplier -2^k is the shift and the byte position at once.  How the value gets
+  // ready for that, cheapest first:
+  //   (A) top byte of its word, right shift: x[sw] >> (24 - s) is exact (IMAD.HI), no ALU-pipe instruction;
+  //   (B) target byte 2 or 3, left shift: x[sw] >> 8 sb has the byte at the bottom and only junk ABOVE it, which the multiply moves
+  //       past the target byte (byte 3 of the even half is discarded, anything beyond bit 31 is gone), no ALU-pipe instruction;
+  //   (C) otherwise x[sw] & mask keeps the bits of the byte that survive the shift (one LOP3); terms of one half that share the
+  //       source word and the net shift 8 (q - sb) + s share the mask and the multiply-add; a net RIGHT shift is an IMAD.HI first.
+  // P6's WeightBasePredictor (previous byte, shifts 0 / -1 / +1 / -1): 4 ALU-pipe + 5 FMA-pipe instructions per word against
+  // 8 + 3 for gather, shift masks and sub_u8x4 -- the plane-major kernels are ALU-pipe bound.  Empty when the form does not apply.
+  std::string lanes_residue_expr(int w) const {
+    if (op != kShift) return std::string();
+    const char* env = getenv("MPC_SPEC_WLANES");
+    if (env && env[0] == '0') return std::string();
+    for (int q = 0; q < 4; q++)
+      if (xsrc[4 * w + q] != 4 * w + q) return std::string();
+    struct Masked { int sw, e; uint32_t mask; };
+    std::string half[2] = {fmt("mpcdev::lanes_even(x[%d])", w), fmt("mpcdev::lanes_odd(x[%d])", w)};
+    std::vector<Masked> masked[2];
+    for (int q = 0; q < 4; q++) {
+      if (w == 0 && q == 0) continue;  // the root byte: the caller puts line[root] there (ResidueModule.cpp:26-27)
+      const int ps = psrc[4 * w + q], s = pval[4 * w + q], sw = ps / 4, sb = ps % 4, h = q & 1;
+      if (std::abs(s) >= 8) continue;  // predicted byte 0
+      if (sb == 3 && s <= 0) {         // (A)
+        half[h] = fmt("mpcdev::mad_fma(mpcdev::shr_fma(x[%d], %d), 0x%08xu, %s)", sw, 24 - s, 0u - (1u << (8 * q)), half[h].c_str());
+      } else if (q >= 2 && s >= 0) {   // (B)
+        const std::string v = sb == 0 ? fmt("x[%d]", sw) : fmt("mpcdev::shr_fma(x[%d], %d)", sw, 8 * sb);
+        half[h] = fmt("mpcdev::mad_fma(%s, 0x%08xu, %s)", v.c_str(), 0u - (1u << (8 * q + s)), half[h].c_str());
+      } else {                         // (C)
+        const int e = 8 * (q - sb) + s;
+        const uint32_t keep = s < 0 ? (uint32_t)((0xff << -s) & 0xff) : (uint32_t)(0xff >> s);
+        bool merged = false;
+        for (auto& t : masked[h])
+          if (t.sw == sw && t.e == e) { t.mask |= keep << (8 * sb); merged = true; }
+        if (!merged) masked[h].push_back({sw, e, keep << (8 * sb)});
+      }
+    }
+    for (int h = 0; h < 2; h++)
+      for (auto& t : masked[h]) {
+        if (t.e >= 0)
+          half[h] = fmt("mpcdev::mad_fma((x[%d] & 0x%08xu), 0x%08xu, %s)", t.sw, t.mask, 0u - (1u << t.e), half[h].c_str());
+        else
+          half[h] = fmt("mpcdev::mad_fma(mpcdev::shr_fma((x[%d] & 0x%08xu), %d), 0xffffffffu, %s)", t.sw, t.mask, -t.e, half[h].c_str());
+      }
+    return fmt("mpcdev::lanes_merge(%s, %s)", half[0].c_str(), half[1].c_str());
+  }
+
   // Predicted word w as ONE byte gather over at most two line words, no arithmetic: *wa, *wb = source words, bytes[q] = (source
   // word, byte) of lane q.  False for predictors that add or shift, or gather from three or four words.
   bool pred_sel_form(int w, std::vector<int>* words, int (&src)[4]) const {
@@ -268,7 +366,10 @@ struct Module {
     const std::string xe = gather_expr("x", srcs), pe = pred_override.empty() ? pred_expr(w) : pred_override;
     std::string e;
     int a = 0, b = 0;
-    if (shared_low && plain_word(xe, &a) && plain_word(pe, &b))
+    const std::string lanes = pred_override.empty() ? lanes_residue_expr(w) : std::string();
+    if (!lanes.empty())
+      e = lanes;
+    else if (shared_low && plain_word(xe, &a) && plain_word(pe, &b))
       e = fmt("sub_u8x4_shared(x[%d], x[%d], ah[%d], ah[%d])", a, b, a, b);
     else
       e = fmt("sub_u8x4(%s, %s)", xe.c_str(), pe.c_str());
@@ -493,12 +594,7 @@ void emit_full(const Module& m, Lines& out, int lut_xor, const RowLayout& lay, c
   } else if (m.family == Module::kBg) {
     for (int j = 0; j < W; j++) out.push_back(fmt("  c[%d] = %s;", j, bg_row_pair_expr(m, lay.ra[j], lay.rb[j]).c_str()));
   } else {
-    for (int h = 0; h < (NCH() + 3) / 4; h++)
-      for (int k = 0; k < 16; k++) {
-        int srcs[4];
-        for (int q = 0; q < 4; q++) srcs[q] = (4 * h + q) < NCH() ? m.cols[16 * (4 * h + q) + k] : -1;  // lines of 32 bytes: two chunks, two zero lanes
-        out.push_back(fmt("  c[%d] = %s;", 16 * h + k, gather_expr("g", srcs).c_str()));
-      }
+    emit_pm_canonical(m.cols, "g", out, false);
   }
   out.push_back("}");
 }
@@ -806,12 +902,7 @@ void emit_pm2_shared(const std::vector<Module>& mods, Lines& out) {
     out.push_back("  }");
   }
   out.push_back("  uint32_t c[32];");
-  for (int h = 0; h < (NCH() + 3) / 4; h++)
-    for (int k = 0; k < 16; k++) {
-      int srcs[4];
-      for (int q = 0; q < 4; q++) srcs[q] = (4 * h + q) < NCH() ? m0.cols[16 * (4 * h + q) + k] : -1;
-      out.push_back(fmt("  c[%d] = %s;", 16 * h + k, gather_expr("r", srcs).c_str()));
-    }
+  emit_pm_canonical(m0.cols, "r", out);
   out.push_back(fmt("  return encode_pm<%d, 0x%04xu, 0x%04xu>(c);", NCH(), sel.first, sel.second));
   out.push_back("}");
   out.push_back("");
@@ -904,6 +995,60 @@ bool build_modules(const mpc_config_pod& cfg, std::vector<Module>* mods, std::st
 }
 
 }  // namespace
+
+// Test hook (tests/test_specgen_residues.py): the residue statements of every PredComp module as plain C++ functions over the
+// host forms of the primitives, next to the module's source tables, so that the generated arithmetic is checked on the CPU
+// against the per-byte definition (PredictorModule.cpp:37-173, ResidueModule.cpp:12-41) before it ever runs on a GPU.
+std::string generate_residue_probe(const mpc_config_pod& cfg, std::string* why) {
+  std::vector<Module> mods;
+  std::string w;
+  if (!build_modules(cfg, &mods, &w)) {
+    if (why) *why = w;
+    return std::string();
+  }
+  Lines out;
+  out.push_back(fmt("static const int kProbeL = %d, kProbeModules = %d;", L, (int)mods.size()));
+  std::vector<std::string> fn, xs, ps, pv, ops, roots;
+  for (auto& m : mods) {
+    out.push_back(fmt("static void probe_res_%d(const uint32_t* x, uint32_t* r) {", m.idx));
+    out.push_back("  uint32_t ah[32];");
+    out.push_back(fmt("  for (int i = 0; i < %d; i++) ah[i] = x[i] | 0x80808080u;", W));
+    out.push_back("  (void)ah;");
+    for (int k = 0; k < W; k++) out.push_back("  { " + m.residue_stmts(k, "rr", true) + fmt(" r[%d] = rr; }", k));
+    out.push_back("}");
+    std::vector<std::string> a, b, c;
+    for (int j = 0; j < L; j++) { a.push_back(fmt("%d", m.xsrc[j])); b.push_back(fmt("%d", m.psrc[j])); c.push_back(fmt("%d", m.pval[j])); }
+    xs.push_back("{" + join(a, ",") + "}");
+    ps.push_back("{" + join(b, ",") + "}");
+    pv.push_back("{" + join(c, ",") + "}");
+    fn.push_back(fmt("probe_res_%d", m.idx));
+    ops.push_back(fmt("%d", (int)m.op));
+    roots.push_back(fmt("%d", m.root));
+  }
+  // the byte transposition of the first plane-major module into the canonical layout of pm_classify (emit_pm_canonical)
+  const Module* pm = nullptr;
+  for (auto& m : mods)
+    if (!pm && m.family == Module::kPm) pm = &m;
+  out.push_back(fmt("static const int kProbeCanonWords = %d;", pm ? 16 * ((NCH() + 3) / 4) : 0));
+  out.push_back("static void probe_canon(const uint32_t* r, uint32_t* c) {");
+  if (pm) emit_pm_canonical(pm->cols, "r", out);
+  out.push_back("  (void)r; (void)c;");
+  out.push_back("}");
+  {
+    std::vector<std::string> cc;
+    for (int i = 0; i < L; i++) cc.push_back(fmt("%d", pm ? pm->cols[i] : 0));
+    out.push_back(fmt("static const int kProbeCols[%d] = {%s};", L, join(cc, ",").c_str()));
+  }
+  out.push_back(fmt("static void (*const kProbeFn[])(const uint32_t*, uint32_t*) = {%s};", join(fn, ", ").c_str()));
+  out.push_back(fmt("static const int kProbeX[][%d] = {%s};", L, join(xs, ",\n  ").c_str()));
+  out.push_back(fmt("static const int kProbeP[][%d] = {%s};", L, join(ps, ",\n  ").c_str()));
+  out.push_back(fmt("static const int kProbeV[][%d] = {%s};", L, join(pv, ",\n  ").c_str()));
+  out.push_back(fmt("static const int kProbeOp[] = {%s};  // 0 copy, 1 add, 2 shift", join(ops, ", ").c_str()));
+  out.push_back(fmt("static const int kProbeRoot[] = {%s};", join(roots, ", ").c_str()));
+  std::string text;
+  for (auto& l : out) { text += l; text += "\n"; }
+  return text;
+}
 
 bool spec_eligible(const mpc_config_pod& cfg, std::string* why) {
   std::vector<Module> mods;

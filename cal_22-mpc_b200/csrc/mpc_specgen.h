@@ -32,4 +32,7 @@ SpecTraits spec_traits(const mpc_config_pod& cfg);
 // jit = true: NVRTC translation unit exposing `extern "C" __global__ mpc_jit_kernel`.  Empty string + *why when not eligible.
 std::string generate_spec_source(const mpc_config_pod& cfg, const std::string& name, bool jit, std::string* why);
 
+// test hook: the residue statements of every PredComp module as host C++ (tests/test_specgen_residues.py); empty + *why when not eligible
+std::string generate_residue_probe(const mpc_config_pod& cfg, std::string* why);
+
 }  // namespace mpc
