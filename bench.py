@@ -18,7 +18,7 @@ against the CPU oracle + totals = sum over ranks), `sustained` (the same launch 
 `configs.mixed4g` (BASELINE configs[2]: 4 GiB mixed dump, F4 and P6; `configs.mixed4g_by_region` = the same classes laid out
 by region, MPC and BDI / FPC / BPC), `configs.short_lines` (32- / 64-byte lines under S32 / S64: specialised vs generic
 kernel), `configs.dump64g` (configs[3]: the 64 GiB dump,
-sharded over the N GPUs), `configs.variants` (configs[4]: BDI / FPC / BPC / SC2 over the mixed dump with the reference's
+sharded over the N GPUs), `configs.variants` (configs[4]: BDI / FPC / BPC / SC2 / PATTERN / CPACK over the mixed dump with the reference's
 CPU rate beside each), `e2e` with the plain host->device copy ceiling of the same run, and `e2e_file` (an .npy in the
 page cache through bin/compressor).
 
@@ -646,6 +646,24 @@ def run_variants(job, d, n):
                       "comp_ratio": tot[0] / tot[1] if tot[1] else None, "table_ms": ms_build, "lookup_ms": ms_apply, "symbols": int(table.n),
                       "includes": f"table from the first {S} lines on rank 0 (device sort + host tree, wall clock" +
                                   (", broadcast" if job.world > 1 else "") + ") + device lookup over every shard"}
+    # PATTERN (the reference's analysis tool) and CPACK carry state from line to line (a cache of lines / a dictionary), so they are
+    # not sharded (replicas only): rank 0 runs them on the head of its shard
+    if job.rank == 0:
+        npat = min(n, 1 << 23)  # 1 GiB: at most as many distinct lines as the reference's cache holds, the temporal count stays on the device
+        ps, ms = None, None
+        for _ in range(2):
+            _, ps, ms = mpcb.pattern_run(device_ptr=d.data_ptr(), n_blocks=npat, device=job.local)
+        res["PATTERN"] = {"value": npat * BLOCK / (ms * 1e-3) / 1e9, "unit": "GB/s", "frac": (npat * BLOCK / (ms * 1e-3) / 1e9) / job.peak,
+                          "lines": npat, "distinct_lines": int(ps.distinct_blocks), "temporal_path": int(ps.temporal_path),
+                          "where": "rank 0 only, first 1 GiB of the dump: analysis kernel + 64-bit hash sort + duplicate pass, device-timed by the library"}
+        ncp = min(n, (64 << 20) // BLOCK)
+        host = d[: ncp * BLOCK].cpu().numpy()
+        t0 = time.perf_counter()
+        _, cs = mpcb.cpack_run(host)
+        dt = time.perf_counter() - t0
+        res["CPACK"] = {"value": ncp * BLOCK / dt / 1e9, "unit": "GB/s", "lines": ncp,
+                        "comp_ratio": cs.original_bits / cs.compressed_bits if cs.compressed_bits else None,
+                        "where": "rank 0 only, first 64 MiB of the dump, ONE host thread: the dictionary persists across lines, sequential by construction"}
     if job.rank == 0 and job.a.cpu_baseline:
         cores = os.cpu_count() or 1
         with mp.get_context("spawn").Pool(cores) as pool:
@@ -655,7 +673,19 @@ def run_variants(job, d, n):
                 info = cpu_reference_pass(None, "mixed_hashed", 31337, n * job.world, job.a.ref_sample_blocks, pool, cores, alg=alg)
                 res[alg]["cpu_reference"] = {"value": info["bytes"] / info["wall_s"] / 1e9, "unit": "GB/s", "cores": cores, "kind": info["kind"],
                                              "sample_blocks": info["bytes"] // BLOCK, "ratio_on_sample": info["ratio"]}
+            for alg, sample in (("PATTERN", 32768), ("CPACK", 262144)):  # stateful: one reference object on one core
+                if not have_ref_alg(alg):
+                    continue
+                info = cpu_reference_pass(None, "mixed_hashed", 31337, n * job.world, sample, pool, 1, alg=alg)
+                res[alg]["cpu_reference"] = {"value": info["bytes"] / info["wall_s"] / 1e9, "unit": "GB/s", "cores": 1, "kind": info["kind"],
+                                             "sample_blocks": info["bytes"] // BLOCK}
     return res
+
+
+def have_ref_alg(alg):
+    """PATTERN / CPACK exist only in the unmodified reference build (the plain-C oracle port times neither through this path)."""
+    from oracle.bridge import have_ref
+    return have_ref()
 
 
 def run_dump64g(job, line):

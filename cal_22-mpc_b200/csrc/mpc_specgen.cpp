@@ -163,6 +163,8 @@ void emit_pm_canonical(const std::vector<int>& cols, const char* arr, Lines& out
   }
 }
 
+int count_prmts(const std::string& e);
+
 // ---- module model --------------------------------------------------------------------------------------------------
 struct Module {
   int idx = 0;
@@ -297,6 +299,10 @@ struct Module {
   // P6's WeightBasePredictor (previous byte, shifts 0 / -1 / +1 / -1): 4 ALU-pipe + 5 FMA-pipe instructions per word against
   // 8 + 3 for gather, shift masks and sub_u8x4 -- the plane-major kernels are ALU-pipe bound.  Empty when the form does not apply.
   std::string lanes_residue_expr(int w) const {
+    // Shifting predictors only.  Plain byte gathers were tried in this form as well (ConsecutiveBasePredictor's byte-plane order: four
+    // source words per predicted word, most of them top bytes, 3 ALU + 8 FMA instead of 7 + 1 per word): fewer ALU-pipe instructions but
+    // more instructions in all, and P6 lost 3-8 % on every data class (profiles/r02_p6_lanes.txt) -- the trade pays only while the
+    // instruction count does not grow.
     if (op != kShift) return std::string();
     const char* env = getenv("MPC_SPEC_WLANES");
     if (env && env[0] == '0') return std::string();
@@ -330,6 +336,15 @@ struct Module {
         else
           half[h] = fmt("mpcdev::mad_fma(mpcdev::shr_fma((x[%d] & 0x%08xu), %d), 0xffffffffu, %s)", t.sw, t.mask, -t.e, half[h].c_str());
       }
+    // ALU-pipe instructions per word: two splits, one merge and the masks here; the gather's PRMTs, one LOP3 per shift distance and
+    // the four of sub_u8x4 in the plain form
+    const int alu_lanes = 3 + (int)(masked[0].size() + masked[1].size());
+    const int psrcs[4] = {psrc[4 * w], psrc[4 * w + 1], psrc[4 * w + 2], psrc[4 * w + 3]};
+    int alu_plain = count_prmts(gather_expr("x", psrcs)) + 4;
+    std::set<int> dist;
+    for (int q = 0; q < 4; q++) dist.insert(pval[4 * w + q]);
+    if (!(dist.size() == 1 && *dist.begin() == 0)) alu_plain += (int)dist.size();
+    if (alu_lanes >= alu_plain) return std::string();
     return fmt("mpcdev::lanes_merge(%s, %s)", half[0].c_str(), half[1].c_str());
   }
 
