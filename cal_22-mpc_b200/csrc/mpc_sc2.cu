@@ -194,12 +194,20 @@ int ws_get(int device, Sc2Workspace** out) {
   if (device < 0 || device >= 16) return fail(MPC_E_ARG, "device index out of range");
   Sc2Workspace& w = g_ws[device];
   if (w.device != device) {
-    SC2_CUDA(cudaMalloc(&w.d_runs, sizeof(int)));
-    SC2_CUDA(cudaMalloc(&w.d_tab_keys, kHashSlots * 4));
-    SC2_CUDA(cudaMalloc(&w.d_tab_lens, kHashSlots));
-    SC2_CUDA(cudaMalloc(&w.d_total, 8));
-    SC2_CUDA(cudaEventCreate(&w.e0));
-    SC2_CUDA(cudaEventCreate(&w.e1));
+    // all or nothing: a failure half way leaves no buffer behind for the next call to leak or to trust
+    cudaError_t e = cudaMalloc(&w.d_runs, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&w.d_tab_keys, kHashSlots * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&w.d_tab_lens, kHashSlots);
+    if (e == cudaSuccess) e = cudaMalloc(&w.d_total, 8);
+    if (e == cudaSuccess) e = cudaEventCreate(&w.e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&w.e1);
+    if (e != cudaSuccess) {
+      cudaFree(w.d_runs); cudaFree(w.d_tab_keys); cudaFree(w.d_tab_lens); cudaFree(w.d_total);
+      if (w.e0) cudaEventDestroy(w.e0);
+      if (w.e1) cudaEventDestroy(w.e1);
+      w.d_runs = nullptr; w.d_tab_keys = nullptr; w.d_tab_lens = nullptr; w.d_total = nullptr; w.e0 = w.e1 = nullptr;
+      return fail(MPC_E_CUDA, std::string("SC2 workspace: ") + cudaGetErrorString(e));
+    }
     w.device = device;
   }
   *out = &w;

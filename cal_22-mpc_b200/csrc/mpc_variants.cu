@@ -45,7 +45,13 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* s_stage = reinterpret_cast<uint4*>(smem_raw);
   __shared__ unsigned long long s_cnt[1 + kCounters];
+  // per-tile counters: one row per warp, written by that warp's lane 0 with plain loads and stores.  64-bit shared-memory atomics
+  // are compare-and-swap loops (ATOMS.CAST.SPIN.64), and with every warp of the CTA on the same few words a finely mixed dump -- up
+  // to nine counters per tile -- spent more time spinning than checking.  A row counts the lines / words of its warp's tiles: far
+  // below 2^32 for any dump one launch admits.
+  __shared__ uint32_t s_wcnt[kWarps][kCounters];
   if (threadIdx.x < 1 + kCounters) s_cnt[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < kWarps * kCounters; i += kThreads) (&s_wcnt[0][0])[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long bits = 0;
@@ -96,16 +102,16 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
 #pragma unroll
       for (int s = 0; s < 9; s++) {
         const uint32_t c = __popc(__ballot_sync(0xffffffffu, (packed >> (4 * s)) & 1ull));
-        if (lane == 0 && c) atomicAdd(&s_cnt[1 + s], (unsigned long long)c);
+        if (lane == 0 && c) s_wcnt[warp][s] += c;
       }
     } else {
 #pragma unroll
       for (int p = 0; p < 8; p++) {
         const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)((packed >> (8 * p)) & 0xffull));
-        if (lane == 0 && c) atomicAdd(&s_cnt[1 + p], (unsigned long long)c);
+        if (lane == 0 && c) s_wcnt[warp][p] += c;
       }
       const uint32_t c = __reduce_add_sync(0xffffffffu, extra);
-      if (lane == 0 && c) atomicAdd(&s_cnt[1 + 7], (unsigned long long)c);  // counts[7] = TotalWords
+      if (lane == 0 && c) s_wcnt[warp][7] += c;  // counts[7] = TotalWords
     }
    }  // sub-lines
   }, n_blocks * (uint64_t)(W / 4));
@@ -121,7 +127,12 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
   for (int o = 16; o; o >>= 1) bits += __shfl_down_sync(0xffffffffu, bits, o);
   if (lane == 0 && bits) atomicAdd(&s_cnt[0], bits);
   __syncthreads();
-  if (threadIdx.x < 1 + kCounters && s_cnt[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < 1 + kCounters) {
+    unsigned long long v = s_cnt[threadIdx.x];
+    if (threadIdx.x >= 1)
+      for (int w = 0; w < kWarps; w++) v += s_wcnt[w][threadIdx.x - 1];
+    if (v) atomicAdd(&stats[threadIdx.x], v);
+  }
 }
 
 thread_local std::string g_verr;
