@@ -105,7 +105,10 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
                unsigned long long* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* s_stage = reinterpret_cast<uint4*>(smem_raw);
-  __shared__ unsigned long long s_cnt[kCnt];
+  // 32-bit words: a 64-bit shared-memory atomicAdd is a compare-and-swap loop, and every warp of the CTA adds to these few words once per
+  // tile.  A CTA sees at most ceil(lines / CTAs) lines and 64 immediates per line: below 2^32 for any dump the 32-bit line index admits
+  // (a grid smaller than the GPU means a dump of a few tiles).
+  __shared__ uint32_t s_cnt[kCnt];
   __shared__ uint32_t s_hist[512];  // [0..255] bytes of all-zero / word-repeating lines, [256..511] bytes of the others
   if (threadIdx.x < kCnt) s_cnt[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < 512; i += kThreads) s_hist[i] = 0;
@@ -151,9 +154,9 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
     const uint32_t cz = __popc(__ballot_sync(0xffffffffu, is_zero)), cr = __popc(__ballot_sync(0xffffffffu, is_rep));
     const uint32_t cu = __popc(__ballot_sync(0xffffffffu, valid && sel == 9));
     if (lane == 0) {
-      if (cz) atomicAdd(&s_cnt[0], (unsigned long long)cz);
-      if (cr) atomicAdd(&s_cnt[1], (unsigned long long)cr);
-      if (cu) atomicAdd(&s_cnt[2], (unsigned long long)cu);
+      if (cz) atomicAdd(&s_cnt[0], cz);
+      if (cr) atomicAdd(&s_cnt[1], cr);
+      if (cu) atomicAdd(&s_cnt[2], cu);
     }
 #pragma unroll
     for (int p = 0; p < 6; p++) {
@@ -161,7 +164,7 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
       const uint32_t c = __popc(__ballot_sync(0xffffffffu, mine));
       if (c) {  // warp-uniform
         const uint32_t s = __reduce_add_sync(0xffffffffu, mine ? imm : 0u);
-        if (lane == 0) { atomicAdd(&s_cnt[3 + p], (unsigned long long)c); atomicAdd(&s_cnt[9 + p], (unsigned long long)s); }
+        if (lane == 0) { atomicAdd(&s_cnt[3 + p], c); atomicAdd(&s_cnt[9 + p], s); }
       }
     }
    }  // sub-lines
@@ -184,7 +187,7 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
     }
   }
   __syncthreads();
-  if (threadIdx.x < kCnt && s_cnt[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < kCnt && s_cnt[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
   for (int i = threadIdx.x; i < 512; i += kThreads)
     if (s_hist[i]) atomicAdd(&stats[kCnt + i], (unsigned long long)s_hist[i]);
 }
@@ -306,6 +309,17 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
   PAT_CUDA(cudaMalloc(&stats.p, kWords * sizeof(unsigned long long)));
   PAT_CUDA(cudaMemset(stats.p, 0, kWords * sizeof(unsigned long long)));
   PAT_CUDA(cudaMalloc(&keys.p, (size_t)(n ? n : 1) * 8));
+  // every buffer of the sort is allocated BEFORE the first kernel: cudaMalloc between two launches leaves the GPU idle for as long as
+  // the allocation takes on the host (milliseconds in a process that already holds most of the memory), inside the timed region
+  size_t tbytes = 0;
+  if (n) {
+    PAT_CUDA(cudaMalloc(&keys2.p, (size_t)n * 8));
+    PAT_CUDA(cudaMalloc(&idx.p, (size_t)n * 4));
+    PAT_CUDA(cudaMalloc(&idx2.p, (size_t)n * 4));
+    PAT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tbytes, (const uint64_t*)keys.p, (uint64_t*)keys2.p, (const uint32_t*)idx.p,
+                                             (uint32_t*)idx2.p, (int)n));
+    PAT_CUDA(cudaMalloc(&temp.p, tbytes ? tbytes : 16));
+  }
   EventPair ev;
   cudaEventRecord(ev.a, 0);
   if (n) {
@@ -330,14 +344,7 @@ static int pattern_run(int device, const uint8_t* d_lines, const uint8_t* h_line
     else if (line_size == 64) PAT_CUDA(launch(pattern_kernel<16>, 2));
     else PAT_CUDA(launch(pattern_kernel<32>, 1));
     // temporal locality: sort (hash, index), confirm equal-hash neighbours on the bytes
-    PAT_CUDA(cudaMalloc(&keys2.p, (size_t)n * 8));
-    PAT_CUDA(cudaMalloc(&idx.p, (size_t)n * 4));
-    PAT_CUDA(cudaMalloc(&idx2.p, (size_t)n * 4));
     iota_kernel<<<(n + 255) / 256, 256>>>((uint32_t*)idx.p, n);
-    size_t tbytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tbytes, (const uint64_t*)keys.p, (uint64_t*)keys2.p, (const uint32_t*)idx.p,
-                                    (uint32_t*)idx2.p, (int)n);
-    PAT_CUDA(cudaMalloc(&temp.p, tbytes ? tbytes : 16));
     PAT_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tbytes, (const uint64_t*)keys.p, (uint64_t*)keys2.p, (const uint32_t*)idx.p,
                                              (uint32_t*)idx2.p, (int)n));
     dup_kernel<<<(n + 255) / 256, 256>>>((const uint64_t*)keys2.p, (const uint32_t*)idx2.p, reinterpret_cast<const uint4*>(d_lines), n,
