@@ -147,8 +147,15 @@ pattern_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
 #pragma unroll
       for (int k = 0; k < 4; k++) atomicAdd(&s_hist[(x[0] >> (8 * k)) & 0xffu], (uint32_t)W);
     } else if (valid) {
+      // a copy of the line that the loop indexes at run time (thread-local memory, L1-resident): the 128 updates are eight iterations
+      // of a four-word body instead of 700 straight-line instructions -- the kernel's footprint was past the instruction cache
+      // (profiles/r02_end_pattern_smooth.txt: more than half of the stall samples were instruction fetches).  Measured per GiB:
+      // unrolled 2.91 ms (smooth) / 3.23 (hash-mixed), one word per iteration 2.35 / 3.70, four 2.00 / 3.34, eight 2.11 / 3.42.
+      uint32_t xl[W];
 #pragma unroll
-      for (int i = 0; i < W; i++) lane_count_word(x[i], my_table, s_bins);
+      for (int i = 0; i < W; i++) xl[i] = x[i];
+#pragma unroll 4
+      for (int i = 0; i < W; i++) lane_count_word(xl[i], my_table, s_bins);
     }
     // warp-aggregated line counters
     const uint32_t cz = __popc(__ballot_sync(0xffffffffu, is_zero)), cr = __popc(__ballot_sync(0xffffffffu, is_rep));

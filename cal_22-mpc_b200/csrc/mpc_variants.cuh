@@ -130,6 +130,67 @@ MPC_HD uint32_t bdi_check(const uint32_t (&x)[32], uint32_t* imm_out = nullptr) 
   return (uint32_t)n + 8u * (imm * (uint32_t)D + ((uint32_t)B + ((uint32_t)n - imm - 1u) * (uint32_t)D));  // wraps when imm == n
 }
 
+// bdi_check with the delta size as a RUN-TIME value (base sizes 8 and 4): one copy of the code per base size instead of one per
+// (base, delta) pair.  The general form of the six checks shrinks from six unrolled bodies to three, and the BDI / PATTERN kernels
+// -- 7 000 / 9 500 SASS instructions, a quarter to a half of their stall samples waiting for instruction fetches -- run the delta
+// sizes of a base size as iterations of one loop.  Same rule, same sizes (tests/test_swar_host.py, tests/test_variants.py).
+template <int B, int W>
+MPC_HD uint32_t bdi_check_rt(const uint32_t (&x)[32], uint32_t D, uint32_t* imm_out) {
+  constexpr int n = 4 * W / B;
+  uint32_t imm = 0;
+  bool not_all = false;
+  if (B == 8) {
+    const uint64_t half = 1ull << (8u * D - 1u);
+    const uint64_t span = 3ull * half;  // x in [-half, 2 half) <=> x + half < 3 half (bdi_fits64)
+    uint64_t base = 0;
+    uint32_t imm_mask = 0;
+#pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+      const uint64_t v = bdi_value<8>(x, i);
+      const bool im = (v + half) < span && v != ~0ull;
+      imm_mask |= (im ? 1u : 0u) << i;
+      base = im ? base : v;
+    }
+    imm = (uint32_t)popc32(imm_mask);
+#pragma unroll
+    for (int g = 0; g < n; g += 4) {
+      if (!not_all) {
+#pragma unroll
+        for (int i = g; i < g + 4; i++) {
+          const uint64_t d = base - bdi_value<8>(x, i);
+          not_all |= !((imm_mask >> i) & 1u) && !((d + half) < span && d != ~0ull);
+        }
+      }
+    }
+  } else {
+    const uint32_t limit = D == 1u ? 0xffu : 0xffffu;  // zero-extended values are never negative
+    const uint32_t half = 1u << (8u * D - 1u);
+    uint32_t base = 0;
+#pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+      const uint32_t v = (uint32_t)bdi_value<B>(x, i);
+      const bool im = v <= limit;
+      imm += im ? 1u : 0u;
+      base = im ? base : v;
+    }
+#pragma unroll
+    for (int g = 0; g < n; g += 8) {
+      if (!not_all) {
+#pragma unroll
+        for (int i = g; i < g + 8; i++) {
+          const uint32_t v = (uint32_t)bdi_value<B>(x, i);
+          const uint32_t d = base - v;
+          const bool fits = v <= base ? d <= 2u * half - 1u : (d + half) <= half - 2u;  // bdi_delta_fits32
+          not_all |= v > limit && !fits;
+        }
+      }
+    }
+  }
+  if (imm_out) *imm_out = imm;
+  if (not_all) return (uint32_t)n + 8u * (imm * D + ((uint32_t)n - imm) * (uint32_t)B);
+  return (uint32_t)n + 8u * (imm * D + ((uint32_t)B + ((uint32_t)n - imm - 1u) * D));  // wraps when imm == n
+}
+
 // ---- the common case in one pass per base size ------------------------------------------------------------------------
 // Most of a dump (floats, pointers, noise) holds NO immediate for any delta size of a base size: then the base is value 0,
 // a check either fits -- every value within a D-byte delta of value 0 -- or costs more than the raw line (n + 8 L bits), and
@@ -224,9 +285,14 @@ MPC_HD uint32_t bdi_best_check(const uint32_t (&x)[32], int* sel, uint32_t* imm,
     else if (need == 2 && best > bdi_fit_size<8, 2, W>()) { best = bdi_fit_size<8, 2, W>(); *sel = 1; *imm = 0; }
     else if (need == 4 && best > bdi_fit_size<8, 4, W>()) { best = bdi_fit_size<8, 4, W>(); *sel = 2; *imm = 0; }
   } else {
-    cur = bdi_check<8, 1, W>(x, &im); if (best > cur) { best = cur; *sel = 0; *imm = im; }
-    if (best > bdi_fit_size<8, 2, W>()) { cur = bdi_check<8, 2, W>(x, &im); if (best > cur) { best = cur; *sel = 1; *imm = im; } }
-    if (best > bdi_fit_size<8, 4, W>()) { cur = bdi_check<8, 4, W>(x, &im); if (best > cur) { best = cur; *sel = 2; *imm = im; } }
+#pragma unroll 1
+    for (int d = 0; d < 3; d++) {  // delta sizes 1, 2, 4: one body (bdi_check_rt)
+      const uint32_t D = 1u << d, n8 = (uint32_t)(W / 2);
+      if (d == 0 || best > n8 + 8u * (8u - D + n8 * D)) {  // bdi_fit_size<8, D, W>
+        cur = bdi_check_rt<8, W>(x, D, &im);
+        if (best > cur) { best = cur; *sel = d; *imm = im; }
+      }
+    }
   }
   if (best > bdi_fit_size<4, 1, W>()) {
     if (fast4) {
@@ -234,8 +300,14 @@ MPC_HD uint32_t bdi_best_check(const uint32_t (&x)[32], int* sel, uint32_t* imm,
       if (need == 1) { best = bdi_fit_size<4, 1, W>(); *sel = 3; *imm = 0; }
       else if (need == 2 && best > bdi_fit_size<4, 2, W>()) { best = bdi_fit_size<4, 2, W>(); *sel = 4; *imm = 0; }
     } else {
-      cur = bdi_check<4, 1, W>(x, &im); if (best > cur) { best = cur; *sel = 3; *imm = im; }
-      if (best > bdi_fit_size<4, 2, W>()) { cur = bdi_check<4, 2, W>(x, &im); if (best > cur) { best = cur; *sel = 4; *imm = im; } }
+#pragma unroll 1
+      for (int d = 0; d < 2; d++) {  // delta sizes 1, 2
+        const uint32_t D = 1u << d, n4 = (uint32_t)W;
+        if (d == 0 || best > n4 + 8u * (4u - D + n4 * D)) {  // bdi_fit_size<4, D, W>
+          cur = bdi_check_rt<4, W>(x, D, &im);
+          if (best > cur) { best = cur; *sel = 3 + d; *imm = im; }
+        }
+      }
     }
   }
   if (best > bdi_fit_size<2, 1, W>()) {
