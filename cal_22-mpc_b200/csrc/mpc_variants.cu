@@ -88,7 +88,7 @@ variant_kernel(const uint4* __restrict__ lines, uint64_t n_blocks, uint16_t* __r
       size = mpcvar::bdi_block_with<W>(x, &st, MakeWarpVote());
       packed = 1ull << (4 * st);  // nine 4-bit one-hot counters
     } else if (ALG == MPC_ALG_FPC) {
-      size = mpcvar::fpc_block<W>(x, &packed);
+      size = mpcvar::fpc_block<W>(x, &packed, WarpVote{0xffffffffu});  // every lane is here
     } else {
       size = mpcvar::bpc_block<W>(x, &packed, &extra);
     }

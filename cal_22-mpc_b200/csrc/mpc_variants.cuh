@@ -381,26 +381,50 @@ MPC_HD uint64_t block_hash64(const uint32_t (&x)[32]) {
 // ---- FPC ------------------------------------------------------------------------------------------------------
 // FPC::CompressLine, FPC.cpp:7-87.  counts8 packs the eight per-word prefix counters, 8 bits each (<= 32 per block).
 // The reference's unbounded zero-run scan (FPC.cpp:26) is bounded at the block end here.
-template <int W = 32>
-MPC_HD uint32_t fpc_block(const uint32_t (&x)[32], uint64_t* counts8) {
+// Branch-free: every lane of a warp holds a different pattern on a mixed dump, and an if / else chain per word made the warp walk
+// every arm (the compiler kept the chain as branches: 86 BRA and 56 BSSY / BSYNC pairs in the 128-byte-line kernel).  Here the
+// tests are range tests -- a word is a sign-extended k-bit value iff (v + 2^(k-1)) < 2^k, both halfwords are sign-extended bytes iff
+// ((h + 0x80) mod 2^16) < 0x100 in each halfword --, the pattern is the first test that holds (a select chain from the back) and its
+// cost comes out of a byte table with one PRMT.  What the chain was good at -- words that are decided by its first arms on EVERY
+// lane (zero pages, small integers) -- is kept by votes: a warp whose lines are all zero is done at once, and the three tests past "sign-extended
+// halfword" are skipped for a word that no lane needs them for (one vote per word; one per four words or one per line measured slower).  `vote(b)` = b holds on every lane of the warp
+// (the identity on the host).
+template <int W = 32, class Vote = BdiSelfVote>
+MPC_HD uint32_t fpc_block(const uint32_t (&x)[32], uint64_t* counts8, const Vote& vote = Vote()) {
+  uint32_t any = 0;
+#pragma unroll
+  for (int i = 0; i < W; i++) any |= x[i];
+  if (vote(any == 0u)) {  // one zero run: 6 bits, W words of pattern 0
+    *counts8 = (uint64_t)W;
+    return 6u;
+  }
   uint32_t size = 0;
   uint64_t cnt = 0;
   bool prev_zero = false;
 #pragma unroll
   for (int i = 0; i < W; i++) {
     const uint32_t v = x[i];
-    int p;
-    uint32_t c;
-    if (v == 0) { p = 0; c = prev_zero ? 0u : 6u; }
-    else if ((v & 0xFFFFFFF8u) == 0 || (v & 0xFFFFFFF8u) == 0xFFFFFFF8u) { p = 1; c = 7; }
-    else if ((v & 0xFFFFFF80u) == 0 || (v & 0xFFFFFF80u) == 0xFFFFFF80u) { p = 2; c = 11; }
-    else if ((v & 0xFFFF8000u) == 0 || (v & 0xFFFF8000u) == 0xFFFF8000u) { p = 3; c = 19; }
-    else if ((v & 0x0000FFFFu) == 0) { p = 4; c = 19; }
-    else if ((v & 0xFF80FF80u) == 0 || (v & 0xFF80FF80u) == 0xFF800000u || (v & 0xFF80FF80u) == 0x0000FF80u ||
-             (v & 0xFF80FF80u) == 0xFF80FF80u) { p = 5; c = 19; }
-    else if (v == (v & 0xffu) * 0x01010101u) { p = 6; c = 11; }
-    else { p = 7; c = 35; }
-    prev_zero = (v == 0);
+    const bool z = v == 0;
+    const bool s16 = (v + 0x8000u) < 0x10000u;  // sign-extended 16 bits (covers 8, 4 and zero)
+    uint32_t p = 7u;
+    if (!vote(s16)) {  // some lane's word is none of the first four patterns
+      p = (v == (v & 0xffu) * 0x01010101u) ? 6u : p;                          // one byte, four times
+      p = ((mpcdev::add_u16x2(v, 0x00800080u) & 0xff00ff00u) == 0u) ? 5u : p;  // two sign-extended bytes in the halfwords
+      p = ((v & 0x0000ffffu) == 0u) ? 4u : p;                                  // low halfword zero
+    }
+    p = s16 ? 3u : p;
+    p = ((v + 0x80u) < 0x100u) ? 2u : p;
+    p = ((v + 0x8u) < 0x10u) ? 1u : p;
+    p = z ? 0u : p;
+    // cost of pattern p (FPC.cpp:16-83): 6 once per zero run, 7, 11, 19, 19, 19, 11, 35
+#if defined(__CUDA_ARCH__)
+    uint32_t c = __byte_perm(0x130b0706u, 0x230b1313u, p) & 0xffu;
+#else
+    const uint32_t kCost[8] = {6, 7, 11, 19, 19, 19, 11, 35};
+    uint32_t c = kCost[p];
+#endif
+    c = (z && prev_zero) ? 0u : c;
+    prev_zero = z;
     size += c;
     cnt += 1ull << (8 * p);
   }
