@@ -188,3 +188,43 @@ def test_bdi_blocks_on_delta_boundaries_match_oracle(swar):
     assert bad.size == 0, (bad[:5], sizes[bad[:5]], want_sizes[bad[:5]])
     assert np.array_equal(counts, want_counts)
     assert len(set(sizes.tolist())) > 8  # the set really exercises several encodings
+
+
+def test_fpc_words_on_pattern_boundaries_match_oracle(swar):
+    """fpc_block selects the pattern with range tests ((v + 2^(k-1)) < 2^k, a packed halfword add) instead of the reference's
+    mask comparisons (FPC.cpp:16-83): every word on either side of every pattern boundary, alone in a line of zeros, after a
+    zero and after a non-zero word, and mixed into random lines."""
+    from oracle.bridge import VARIANT_ID, oracle_variant
+    M = 0xFFFFFFFF
+    words = {0, 1, 0x01010101, 0x7F7F7F7F, 0x80808080, 0xFFFFFFFF, 0x00FF00FF, 0xFF00FF00, 0x00010000, 0xFFFF0000, 0x0000FFFF}
+    for k in (3, 7, 15, 16, 23, 31):  # sign-extension limits of 4 / 8 / 16 bits and the halfword / byte seams
+        for d in (-2, -1, 0, 1, 2):
+            words.add(((1 << k) + d) & M)
+            words.add((-(1 << k) + d) & M)
+    for hi in (0x0000, 0x007F, 0x0080, 0x00FF, 0xFF7F, 0xFF80, 0xFFFF, 0x8000, 0x7FFF, 0x0100):  # two sign-extended bytes or not
+        for lo in (0x0000, 0x007F, 0x0080, 0x00FF, 0xFF7F, 0xFF80, 0xFFFF, 0x8000, 0x7FFF, 0x0100):
+            words.add((hi << 16) | lo)
+    for b in (0x00, 0x01, 0x7F, 0x80, 0xFE, 0xFF):  # one byte four times, and one byte off
+        words.add(b * 0x01010101)
+        words.add((b * 0x01010101) ^ 0x00010000)
+    words = sorted(words)
+    rng = np.random.default_rng(5)
+    lines = []
+    for w in words:
+        a = np.zeros(32, np.uint32); a[5] = w; lines.append(a)                      # alone: zero runs on both sides
+        a = np.zeros(32, np.uint32); a[0] = w; a[1] = w; a[31] = w; lines.append(a)  # first / repeated / last word
+        a = rng.integers(0, 1 << 32, 32, dtype=np.uint64).astype(np.uint32); a[rng.integers(0, 32)] = w; lines.append(a)
+    d = np.ascontiguousarray(np.stack(lines)).view(np.uint8).reshape(-1, 128)
+    want_sizes, want_counts = oracle_variant("FPC", d)
+    sizes = np.zeros(d.shape[0], np.uint32)
+    counts = np.zeros(16, np.uint64)
+    swar.t_variant_run.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+    swar.t_variant_run(VARIANT_ID["FPC"], d.ctypes.data, d.shape[0], sizes.ctypes.data, counts.ctypes.data)
+    bad = np.nonzero(sizes != want_sizes)[0]
+    assert bad.size == 0, (bad[:5], sizes[bad[:5]], want_sizes[bad[:5]])
+    assert np.array_equal(counts, want_counts)
+    assert all(want_counts[p] > 0 for p in range(8))  # every pattern occurs
+    from oracle.bridge import RefCompressor, have_ref
+    if have_ref():  # and the unmodified reference says the same on these lines
+        ref_sizes, _ = RefCompressor("FPC").compress(d, want_sels=False)
+        assert np.array_equal(ref_sizes, want_sizes)
