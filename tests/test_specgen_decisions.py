@@ -40,6 +40,20 @@ def test_plane_major_probe_config_takes_the_state_machine_form(generated):
     assert src.count("pm2_tail(") == 2 and "encode_pm<8," in src  # defined once, called once
 
 
+def test_plane_major_probe_config_trades_alu_for_fma_instructions(generated):
+    """P6's Weight module takes the 16-bit-lane residue (shifts and byte positions as multiply-adds), its canonical layout the 4 x 4
+    byte transposes; the plain-copy predictors keep the byte-wise subtract (the lane form measured slower there), and E5 -- one
+    plane-major module among column-major ones, at its register limit -- keeps the per-word gathers."""
+    src = generated["P6"]
+    res5 = src[src.index("uint32_t res_5("):src.index("// leading zero rows from complete residues")]
+    assert res5.count("mpcdev::lanes_merge(") == 32 and "shiftmix(" not in res5 and "sub_u8x4(" not in res5
+    res2 = src[src.index("uint32_t res_2("):src.index("uint32_t res_3(")]
+    assert "lanes_merge" not in res2 and res2.count("sub_u8x4(") == 32
+    tail = src[src.index("uint32_t pm2_tail("):src.index("struct Cfg {")]
+    assert tail.count("0x5140u") == 16 and tail.count("0x7362u") == 16  # eight groups of four residue words, both stages
+    assert "0x5140u" not in generated["E5"]
+
+
 def test_column_major_config_gets_lut_paired_rows_and_selector_groups(generated):
     src = generated["F4"]
     assert "kUseLut = true" in src and "kLutXor = 1" in src and "kWarps = 20" in src
