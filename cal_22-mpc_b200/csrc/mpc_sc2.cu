@@ -11,6 +11,9 @@
 // CPACK (CPACK.cpp:7-101) carries a 16-entry FIFO dictionary across lines, so its result depends on the order of
 // all earlier words: it is sequential by construction and runs on the host (mpc_cpack_run_host).
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>  // host side of CPACK: the sixteen dictionary entries are searched with two compares
+#endif
 
 #include <algorithm>
 #include <cstring>
@@ -429,9 +432,11 @@ extern "C" int mpc_cpack_run_host(const uint8_t* h_lines, uint64_t n_blocks, uin
   if (!out || (n_blocks && !h_lines) || line_size % 4) return MPC_E_ARG;
   static const uint32_t kLen[6] = {2, 34, 6, 24, 12, 16};
   uint32_t dict[16] = {0};  // FIFO, oldest at `head`; words kept as little-endian 32-bit values
+  alignas(16) uint16_t low[16] = {0};  // their low halfwords: what a dictionary match is decided on (bytes 0-1, CPACK.cpp:45-70)
   int head = 0;
   memset(out, 0, sizeof(*out));
   const uint32_t W = line_size / 4;
+  uint64_t counts[6] = {0, 0, 0, 0, 0, 0};
   for (uint64_t b = 0; b < n_blocks; b++) {
     uint32_t size = 0;
     for (uint32_t i = 0; i < W; i++) {
@@ -441,22 +446,38 @@ extern "C" int mpc_cpack_run_host(const uint8_t* h_lines, uint64_t n_blocks, uin
       if ((w & 0x00ffffffu) == 0) {
         pat = (w == 0) ? 0 : 4;  // zzzz / zzzx
       } else {
+        // the first entry, oldest first, whose bytes 0-1 equal the word's
+#if defined(__SSE2__)
+        // all sixteen entries at once: compare the halfwords, one bit per entry, rotated so that bit 0 is the oldest entry
+        const __m128i key = _mm_set1_epi16((short)(w & 0xffffu));
+        const __m128i e0 = _mm_cmpeq_epi16(_mm_load_si128(reinterpret_cast<const __m128i*>(low)), key);
+        const __m128i e1 = _mm_cmpeq_epi16(_mm_load_si128(reinterpret_cast<const __m128i*>(low + 8)), key);
+        const uint32_t m = (uint32_t)_mm_movemask_epi8(_mm_packs_epi16(e0, e1));  // bit j = entry j matches
+        const uint32_t r = ((m >> head) | (m << (16 - head))) & 0xffffu;
+        if (r) {
+          const uint32_t x = w ^ dict[(head + __builtin_ctz(r)) & 15];
+          pat = (x & 0x00ff0000u) ? 3 : ((x & 0xff000000u) ? 5 : 2);
+        }
+#else
         for (int j = 0; j < 16 && pat < 0; j++) {
           const uint32_t d = dict[(head + j) & 15];
           if (((w ^ d) & 0x0000ffffu) == 0) pat = ((w ^ d) & 0x00ff0000u) ? 3 : (((w ^ d) & 0xff000000u) ? 5 : 2);
         }
+#endif
         if (pat < 0) {
           pat = 1;
           dict[head] = w;
+          low[head] = (uint16_t)(w & 0xffffu);
           head = (head + 1) & 15;
         }
       }
       size += kLen[pat];
-      out->counts[pat]++;
+      counts[pat]++;
     }
     if (h_sizes) h_sizes[b] = (uint16_t)size;
     out->compressed_bits += size;
   }
+  for (int p = 0; p < 6; p++) out->counts[p] = counts[p];
   out->blocks = n_blocks;
   out->original_bits = n_blocks * 8ull * line_size;
   return MPC_OK;
